@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — RGB-D frames fused/sec @1080x1920 (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] — TSDF integration of 300 synthetic
+1080x1920 frames (tunnel T1, known poses, 1 cm voxels, 8^3 blocks, trunc 4 cm,
+depth_max 5 m) on one B200.  One "step" = reset the volume and fuse all 300
+frames (K4 touch/allocate + K5 integrate, 32-frame temporally blocked passes).
+N>1: every rank fuses its own 300-frame stretch of the tunnel (frame-stream
+sharding, weak scaling), then blocks outside a rank's z-slab are routed to their
+owner over NCCL and merged.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with frames resident
+in HBM; `e2e` = same through the host-buffer API with H2D copies + a D2H result
+read inside the timed region; `roofline` = K5 integrate kernel, algorithmic bytes
+(40*V_upd + 7*H*W + 16*B per frame) / CUDA-event time of that kernel;
+`cpu_baseline` = the oracle (OpenMP C port of the same semantics) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W = 1920, 1080
+KINTR = (1719.0, 1719.0, 540.0, 960.0)
+VOXEL, TRUNC, DEPTH_MAX = 0.01, 0.04, 5.0
+NOISE = 0.002
+SEED = 1234
+METRIC = "RGB-D frames fused/sec @1080x1920 (TSDF integration, cfg2)"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """CPU arm: the oracle (C/OpenMP restatement of the same TSDF semantics — the reference
+    has no TSDF code and is pure Python, so nothing compiles into oracle/_ref) on all host
+    cores, each step a bounded sample of the same workload."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from oracle import capi
+    frames = make_host_frames(args.cpu_frames, first=0)
+    cores = capi.num_threads()
+
+    def step():
+        ov = capi.TSDFVolume(VOXEL, TRUNC)
+        for d, c, T in frames:
+            ov.integrate(d, c, KINTR, T, 1.0, DEPTH_MAX)
+        return ov
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ov = step()
+    dt = time.perf_counter() - t0
+    fps = args.steps * len(frames) / dt
+    sample = f"first {len(frames)} of the 300 cfg2 frames per step (reset + touch + integrate), {cores} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (tunnel T1, seed 1234; frames generated once, outside the timed region)",
+        "config": workload_config(len(frames), 1),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "blocks": int(ov.num_blocks),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_host_frames(n, first=0):
+    """Host copies of cfg2 frames [first, first+n): device generator when a GPU is there
+    (data creation only), NumPy twin otherwise."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    out = []
+    if has_gpu:
+        from textureless_3d_reconstruction_b200.runtime import get_context
+        ctx = get_context(0)
+        for i in range(first, first + n):
+            d, c, T = ctx.synth_frame(0, i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE)
+            out.append((d.cpu().numpy(), c.cpu().numpy(), T))
+    else:
+        from textureless_3d_reconstruction_b200 import synthetic as S
+        for i in range(first, first + n):
+            out.append(S.synth_frame(0, i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE))
+    return out
+
+
+def workload_config(frames, world):
+    return {"workload": "BASELINE configs[1]: TSDF integration, 300 synthetic 1080x1920 frames, 1 cm voxels, "
+                        "8^3 blocks, trunc 4 cm, depth_max 5 m, known poses",
+            "frames_per_step_per_gpu": frames, "H": H, "W": W, "voxel_size": VOXEL, "sdf_trunc": TRUNC,
+            "depth_max": DEPTH_MAX, "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU",
+            "l2": "inputs (4.35 GB of frames per step) exceed the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume, get_context
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = get_context(local)
+    dev = ctx.device
+    F, B = args.frames, args.batch
+    first = rank * F  # rank r fuses frames [r*F, (r+1)*F) of the tunnel
+
+    # ---- stage the frames in HBM (outside the timed region)
+    depth_all = torch.empty((F, H, W), dtype=torch.float32, device=dev)
+    bgr_all = torch.empty((F, H, W, 3), dtype=torch.uint8, device=dev)
+    poses = []
+    for i in range(F):
+        _, _, T = ctx.synth_frame(0, first + i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE,
+                                  depth=depth_all[i], bgr=bgr_all[i])
+        poses.append(T)
+    torch.cuda.synchronize()
+    vol = TSDFVolume(VOXEL, TRUNC, block_capacity=args.block_capacity, ctx=ctx)
+    views = vol.make_frame_views([depth_all[i] for i in range(F)], [bgr_all[i] for i in range(F)],
+                                 [KINTR] * F, poses)
+
+    router = None
+    if world > 1:
+        from textureless_3d_reconstruction_b200.distributed import BlockRouter
+        router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
+
+    def step():
+        vol.reset()
+        for s in range(0, F, B):
+            vol.integrate_views(views, s, min(B, F - s), H, W, False, 1.0, DEPTH_MAX)
+        if router is not None:
+            router.route()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local)
+    sampler.start()
+    vol.set_profiling(True)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    launches = ctx.launch_count() - l0
+    prof = vol.get_profile()
+    vol.set_profiling(False)
+    cnt = vol.counters(detailed=True)      # counters of the LAST step (reset each step)
+    nblocks = vol.num_blocks
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_frames = F * world * args.steps
+    fps = total_frames / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K5 integrate), per launch
+    peak, peak_src = load_peaks()
+    calls_per_step = -(-F // B)
+    alg_bytes_step = 40 * cnt["voxel_updates"] + 7 * H * W * F + 16 * cnt["block_frames"]
+    min_bytes_step = 40 * cnt["voxels_changed_per_visit"] + 7 * H * W * F + 16 * cnt["block_visits"]
+    k5_ms_per_launch = prof["integrate_ms"] / max(prof["calls"], 1)
+    k4_ms_per_launch = prof["touch_ms"] / max(prof["calls"], 1)
+    achieved = (alg_bytes_step / calls_per_step) / (k5_ms_per_launch * 1e-3) / 1e9
+    roofline = {
+        "kernel": "integrate_kernel (K5)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes_step / calls_per_step,
+        "avg_launch_ms": k5_ms_per_launch, "launches_timed": prof["calls"],
+        "temporal_blocking": {
+            "frames_per_launch": B,
+            "note": "one launch applies up to 32 frames to a block held in registers, so the block state "
+                    "(40 B/voxel) crosses HBM once per launch instead of once per frame; `achieved` uses the "
+                    "per-frame SURVEY 8d byte count and can therefore exceed the copy peak",
+            "batched_min_bytes_per_launch": min_bytes_step / calls_per_step,
+            "achieved_on_batched_min_bytes": (min_bytes_step / calls_per_step) / (k5_ms_per_launch * 1e-3) / 1e9,
+        },
+        "k4_touch_avg_launch_ms": k4_ms_per_launch,
+        "k5_share_of_step": prof["integrate_ms"] / max(ms, 1e-9),
+        "per_frame": {"voxel_updates": cnt["voxel_updates"] / F, "block_frames": cnt["block_frames"] / F},
+    }
+
+    # ---- e2e: host buffers -> H2D -> fuse -> D2H result, through the public API
+    e2e = run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist if world > 1 else None)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args, depth_all, bgr_all, poses)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (tunnel T1, sigma=2 mm depth noise, seed 1234, generated on device)",
+            "config": workload_config(F, world), "clocks": sampler.result(), "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "blocks_per_gpu": int(nblocks), "batch_frames": B,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist):
+    """Frames start in pinned host memory; every step copies all of them to the GPU
+    (double-buffered chunks on a copy stream, overlapped with fusion), fuses, and reads
+    the step's result (voxel-update / block counters) back to the host."""
+    import torch
+    dev = ctx.device
+    F, B = args.frames, args.batch
+    h_depth = torch.empty((F, H, W), dtype=torch.float32, pin_memory=True)
+    h_bgr = torch.empty((F, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    h_depth.copy_(depth_all)
+    h_bgr.copy_(bgr_all)
+    torch.cuda.synchronize()
+    nbuf = 2
+    d_depth = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    d_bgr = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    chunks = [(s, min(B, F - s)) for s in range(0, F, B)]
+    views = []
+    for ci, (s, n) in enumerate(chunks):
+        b = ci % nbuf
+        views.append(vol.make_frame_views([d_depth[b][j] for j in range(n)], [d_bgr[b][j] for j in range(n)],
+                                          [KINTR] * n, poses[s:s + n]))
+    copied = [torch.cuda.Event() for _ in chunks]
+    freed = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def step():
+        vol.reset()
+        for ci, (s, n) in enumerate(chunks):
+            b = ci % nbuf
+            with torch.cuda.stream(copy_stream):
+                if ci >= nbuf:
+                    copy_stream.wait_event(freed[b])
+                d_depth[b][:n].copy_(h_depth[s:s + n], non_blocking=True)
+                d_bgr[b][:n].copy_(h_bgr[s:s + n], non_blocking=True)
+                copied[ci].record(copy_stream)
+            main.wait_event(copied[ci])
+            vol.integrate_views(views[ci], 0, n, H, W, False, 1.0, DEPTH_MAX)
+            freed[b].record(main)
+        return vol.counters()          # synchronous D2H read of the step's result
+
+    steps = max(2, min(args.steps, 5))
+    step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del h_depth, h_bgr
+    return {"value": F * world * steps / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(F * H * W * 7), "d2h_bytes_per_step": 40, "steps": steps,
+            "ms_per_step": ms / steps, "result": res,
+            "api": "TSDFVolume.integrate_views over pinned-host frames (H2D double-buffered) + counters() D2H"}
+
+
+def cpu_baseline(args, depth_all, bgr_all, poses):
+    from oracle import capi
+    n = args.cpu_frames
+    frames = [(depth_all[i].cpu().numpy(), bgr_all[i].cpu().numpy(), poses[i]) for i in range(n)]
+    cores = capi.num_threads()
+    ov = capi.TSDFVolume(VOXEL, TRUNC)
+    ov.integrate(*frames[0][:2], KINTR, frames[0][2], 1.0, DEPTH_MAX)   # warm-up (page faults, alloc)
+    ov = capi.TSDFVolume(VOXEL, TRUNC)
+    t0 = time.perf_counter()
+    for d, c, T in frames:
+        ov.integrate(d, c, KINTR, T, 1.0, DEPTH_MAX)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} of the 300 frames (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s",
+            "voxel_updates": ov.counters()["voxel_updates"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--block-capacity", type=int, default=600_000)
+    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

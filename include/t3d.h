@@ -1,0 +1,284 @@
+/*
+ * t3d.h — C ABI of libt3d.so, the B200 (sm_100a) dense geometric core.
+ *
+ * This is the drop-in boundary for the hot path behind the reference's
+ * depth_to_reconstruction.py (d2r), depth_enhanced_reconstruction.py (der) and
+ * depth_processor.py (dp).  The reference is pure Python and has no FFI of its
+ * own; every entry point below cites the reference function it
+ * replaces.  INTEGRATION.md shows the ctypes stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch/C++ types.
+ *   - All data pointers are DEVICE pointers unless the name ends in `_h`
+ *     (host).  The caller owns every buffer; the library never frees caller
+ *     memory and only allocates its own ctx / volume storage.
+ *   - Every call takes a `t3d_stream` (a cudaStream_t passed as void*) and is
+ *     asynchronous w.r.t. the host unless documented otherwise.
+ *   - Return value: 0 = OK, negative = error (T3D_E_*).  t3d_last_error()
+ *     returns a thread-local message.  No exceptions cross the boundary.
+ *   - One t3d_ctx per process/GPU.  A ctx is not thread-safe; distinct ctxs are.
+ *   - There is NO CPU fallback: without a CUDA device every compute call
+ *     returns T3D_E_CUDA.
+ */
+#ifndef T3D_H_
+#define T3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T3D_VERSION 100
+
+#define T3D_OK 0
+#define T3D_E_INVALID (-1)  /* bad argument */
+#define T3D_E_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define T3D_E_CAPACITY (-3) /* hash table / block pool / output buffer too small */
+#define T3D_E_IO (-4)       /* file I/O */
+#define T3D_E_NUMERIC (-5)  /* voxel index overflow etc. */
+
+typedef struct t3d_ctx t3d_ctx;
+typedef struct t3d_tsdf t3d_tsdf;
+typedef void* t3d_stream; /* cudaStream_t */
+
+const char* t3d_last_error(void);
+int t3d_version(void);
+
+/* Create / destroy the per-GPU context (scratch buffers, scan state, cached
+ * projection-factor tables = the reference's `_projection_cache`, d2r:285-295). */
+t3d_ctx* t3d_create(int device);
+void t3d_destroy(t3d_ctx* ctx);
+/* Number of library kernels launched through this ctx (and its volumes) since
+ * creation — bench.py's `gpu_launches` evidence. */
+int64_t t3d_launch_count(const t3d_ctx* ctx);
+
+/* ------------------------------------------------------------------------- */
+/* K1 — back-projection.                                                      */
+/* Replaces DenseReconstructor.depth_to_pointcloud (d2r:328-384),             */
+/* DensePointCloudGenerator.depth_to_pointcloud (der:554-613) and             */
+/* PointCloudGenerator.generate (dp:371-422).                                 */
+/* ------------------------------------------------------------------------- */
+typedef struct t3d_backproject_params {
+  int32_t H, W;          /* full-resolution frame; depth is H*W C-order        */
+  int32_t subsample;     /* [::s, ::s] slice (d2r:349-353), >= 1               */
+  int32_t depth_is_f64;  /* 0: depth is float32, 1: float64 (der passes        */
+                         /*    depths[i]*scale = f64, der:1135)                */
+  int32_t scale_is_f64;  /* NumPy promotion of `depth*scale` (d2r:356): 0 =    */
+                         /*    python-float scale (stays f32, thresholds cast  */
+                         /*    to f32), 1 = np.float64 scale (everything f64)  */
+  int32_t has_pose;      /* 0: pose=None (points stay in the camera frame)     */
+  int32_t rgb_out_f32;   /* 0: uint8 RGB (d2r/der); 1: float32 RGB in [0,1]    */
+                         /*    = u8.astype(f32)/255 (dp:417)                   */
+  int32_t has_color;     /* 0: bgr==NULL, no colours written (dp rgb=None)     */
+  double fx, fy, cx, cy; /* pinhole intrinsics (d2r:48-51)                     */
+  double scale;          /* depth multiplier (d2r:356); 1.0 for der/dp         */
+  double min_depth, max_depth; /* strict inequalities (d2r:359-361)           */
+  double R[9];           /* world->camera rotation, row-major (d2r:371-376)    */
+  double t[3];           /* world->camera translation                          */
+} t3d_backproject_params;
+
+/* depth: H*W (f32|f64), bgr: H*W*3 u8 (BGR, OpenCV order), conf_mask:
+ * nullable H*W u8 (extension: pixel kept only if non-zero; the reference has no
+ * confidence map).  out_xyz: capacity*3 f32; out_rgb: capacity*3
+ * (u8|f32).  capacity must be >= ceil(H/s)*ceil(W/s) or the call fails.
+ * out_n: device int64, number of valid points.  Output order = row-major order
+ * of the valid sampled pixels (NumPy boolean-mask order, d2r:364-366). */
+int t3d_backproject(t3d_ctx* ctx, const void* depth, const uint8_t* bgr,
+                    const uint8_t* conf_mask, const t3d_backproject_params* p,
+                    float* out_xyz, void* out_rgb, int64_t capacity,
+                    int64_t* out_n, t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K2 — voxel-grid downsample.  Replaces Open3D                               */
+/* PointCloud.voxel_down_sample as called by merge_pointclouds (d2r:405-410,  */
+/* der:635-640).  Semantics: SURVEY §8c R2.                                   */
+/* ------------------------------------------------------------------------- */
+/* xyz: n*3 (f32|f64), rgb: n*3 u8 (nullable).  out_xyz: cap*3 f64 voxel
+ * means; out_rgb: cap*3 u8 = trunc(mean(c/255)*255) (d2r:417-418); out_rgb_sum
+ * (nullable) cap*3 u32 integer colour sums; out_count (nullable) cap u32;
+ * out_vox_idx (nullable): cap*3 int32 voxel indices floor((p-minb)/v).
+ * out_m: device int64.  min_bound_h (nullable, host): if given it is used as
+ * the grid origin `minb` instead of min(p) - v/2 (multi-GPU: the global min).
+ * sorted!=0: output in ascending (ix,iy,iz) order (deterministic); otherwise
+ * hash-slot order.  Synchronous w.r.t. the host (needs the global bounds). */
+int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f64,
+                         const uint8_t* rgb, int64_t n, double voxel,
+                         const double* min_bound_h, int sorted,
+                         double* out_xyz, uint8_t* out_rgb,
+                         uint32_t* out_rgb_sum, uint32_t* out_count,
+                         int32_t* out_vox_idx, int64_t capacity,
+                         int64_t* out_m, double* out_min_bound_h,
+                         t3d_stream stream);
+
+/* Min / max bound of a cloud (host result, synchronous). */
+int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t n,
+               double* min_h, double* max_h, t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K3 — statistical outlier removal.  Replaces Open3D                         */
+/* remove_statistical_outlier(nb_neighbors, std_ratio) (d2r:413-415), R3.     */
+/* ------------------------------------------------------------------------- */
+/* xyz: n*3 f64.  out_mean_dist (nullable): n f64 mean distance to the nb
+ * nearest neighbours (self included).  keep_mask: n u8.  out_kept: device
+ * int64.  stats_h (nullable, host, 3 doubles): mu, sigma, threshold.
+ * Synchronous. */
+int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t n, int nb,
+                            double std_ratio, double* out_mean_dist,
+                            uint8_t* keep_mask, int64_t* out_kept,
+                            double* stats_h, t3d_stream stream);
+
+/* Ordered compaction of rows by a byte mask (keeps input order, R3). */
+int t3d_compact_rows(t3d_ctx* ctx, const void* rows, int64_t n,
+                     int32_t row_bytes, const uint8_t* keep_mask,
+                     void* out_rows, int64_t* out_n, t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K4/K5/K6 — TSDF voxel-block grid (north_star; Open3D                       */
+/* t.geometry.VoxelBlockGrid semantics).  No reference code */
+/* exists for this part: parity is against oracle/ only ("parity unpinned").  */
+/* ------------------------------------------------------------------------- */
+typedef struct t3d_tsdf_params {
+  float voxel_size;      /* metres (config 2: 0.01)                            */
+  float sdf_trunc;       /* metres (config 2: 0.04)                            */
+  int32_t block_res;     /* must be 8                                          */
+  int32_t pixel_round;   /* 0: ui=floor(u+0.5); 1: ui=(int)u       */
+  int64_t block_capacity;/* max voxel blocks resident (10 KiB each)            */
+  int64_t hash_capacity; /* 0 = auto (next pow2 >= 2*block_capacity)           */
+} t3d_tsdf_params;
+
+typedef struct t3d_frame_view {
+  const void* depth;     /* H*W, f32 metres-scale or u16 raw                   */
+  const uint8_t* bgr;    /* H*W*3 u8 BGR (nullable: no colour integration)     */
+  float K[4];            /* fx, fy, cx, cy                                     */
+  float T_cw[12];        /* world->camera extrinsic, row-major 3x4 [R|t]       */
+} t3d_frame_view;
+
+int t3d_tsdf_create(t3d_ctx* ctx, const t3d_tsdf_params* p, t3d_tsdf** out);
+void t3d_tsdf_destroy(t3d_tsdf* v);
+/* Forget all blocks (O(hash) memset; block storage is lazily re-initialised). */
+int t3d_tsdf_reset(t3d_tsdf* v, t3d_stream stream);
+
+/* Fuse `n_frames` (1..32) frames in one pass: K4 touch/allocate over all of
+ * them, then K5 integrates every touched block, each voxel applying its
+ * frames in index order (identical arithmetic to n_frames sequential calls).
+ * frames_h: host array.  depth_is_u16: depth = raw/depth_scale.  Asynchronous. */
+int t3d_tsdf_integrate(t3d_tsdf* v, const t3d_frame_view* frames_h,
+                       int n_frames, int H, int W, int depth_is_u16,
+                       float depth_scale, float depth_max, t3d_stream stream);
+
+/* K4 alone: unique block keys touched by one frame (R4).  out_keys: cap*3
+ * int32; out_n device int64.  Does not modify the volume. */
+int t3d_tsdf_touch(t3d_tsdf* v, const t3d_frame_view* frame_h, int H, int W,
+                   int depth_is_u16, float depth_scale, float depth_max,
+                   int32_t* out_keys, int64_t capacity, int64_t* out_n,
+                   t3d_stream stream);
+
+/* Synchronous getters. */
+int64_t t3d_tsdf_num_blocks(t3d_tsdf* v, t3d_stream stream);
+/* counters_h (5 x int64): [0] voxel updates applied since create/reset
+ * (sum of V_upd), [1] block-frame pairs integrated (sum of B), [2] frames
+ * integrated, [3] voxels changed per block visit (a voxel updated by several
+ * frames of one batch counts once), [4] block visits (one per block per batch). */
+int t3d_tsdf_counters(t3d_tsdf* v, int64_t* counters_h, t3d_stream stream);
+
+/* Per-kernel timing for bench.py's roofline: when enabled every
+ * t3d_tsdf_integrate call is bracketed by CUDA events on its stream.
+ * get_profile synchronises the stream and returns accumulated
+ * {K4 touch ms, K5 integrate ms, integrate calls} since set_profiling. */
+int t3d_tsdf_set_profiling(t3d_tsdf* v, int enable);
+int t3d_tsdf_get_profile(t3d_tsdf* v, double* out3_h, t3d_stream stream);
+
+/* Dump blocks for parity / routing.  keys: B*3 int32; tsdf, weight: B*512 f32
+ * (x fastest, then y, z); rgb: B*512*3 f32 (0..255).  Any output may be NULL. */
+int t3d_tsdf_export_blocks(t3d_tsdf* v, int32_t* keys, float* tsdf,
+                           float* weight, float* rgb, int64_t capacity,
+                           int64_t* out_b, t3d_stream stream);
+/* Merge partial blocks into the volume (multi-GPU owner reduce):
+ * w' = w_a + w_b, tsdf' = (w_a*tsdf_a + w_b*tsdf_b)/w', same for rgb. */
+int t3d_tsdf_merge_blocks(t3d_tsdf* v, const int32_t* keys, const float* tsdf,
+                          const float* weight, const float* rgb, int64_t b,
+                          t3d_stream stream);
+
+/* K6: surface points (R6).  xyz/nrm: cap*3 f32; rgb: cap*3 u8 (nullable
+ * nrm/rgb).  out_n device int64.  Order: deterministic only as a set. */
+int t3d_tsdf_extract_points(t3d_tsdf* v, float weight_threshold, float* xyz,
+                            float* nrm, uint8_t* rgb, int64_t capacity,
+                            int64_t* out_n, t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K7 — normal estimation (north_star; Open3D estimate_normals KNN, R7).      */
+/* ------------------------------------------------------------------------- */
+/* xyz: n*3 f32; nrm: n*3 f32.  orient_to_h (nullable host double[3]): flip
+ * each normal towards that camera location.  Synchronous (grid build). */
+int t3d_estimate_normals(t3d_ctx* ctx, const float* xyz, int64_t n, int knn,
+                         const double* orient_to_h, float* nrm,
+                         t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K8 — point-to-plane ICP (north_star; Open3D registration_icp with          */
+/* TransformationEstimationPointToPlane, R8).                                 */
+/* ------------------------------------------------------------------------- */
+typedef struct t3d_icp_result {
+  double T[16];       /* source->target transform, row-major 4x4               */
+  double fitness;     /* |C| / |S|                                             */
+  double inlier_rmse; /* sqrt(sum d^2 / |C|)                                   */
+  int32_t iterations; /* iterations executed                                   */
+  int32_t converged;
+  int64_t correspondences;
+} t3d_icp_result;
+
+/* src: n_src*3 f32; tgt, tgt_nrm: n_tgt*3 f32.  T0_h: host row-major 4x4.
+ * Synchronous (per-iteration 6x6 solve on the host in f64). */
+int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_src,
+                           const float* tgt, const float* tgt_nrm,
+                           int64_t n_tgt, double max_corr_dist,
+                           const double* T0_h, int max_iter,
+                           double rel_fitness, double rel_rmse,
+                           t3d_icp_result* result_h, t3d_stream stream);
+
+/* One ICP linearisation: correspondences + 6x6 normal equations only.
+ * out27_h: 21 upper-triangular JtJ + 6 Jtr; out_stats_h: sum r^2 (squared
+ * point distance), count.  Used by the multi-GPU path (all-reduce of 29
+ * doubles between linearise and solve). */
+int t3d_icp_linearize(t3d_ctx* ctx, const float* src, int64_t n_src,
+                      const float* tgt, const float* tgt_nrm, int64_t n_tgt,
+                      double max_corr_dist, const double* T_h,
+                      double* out27_h, double* out_stats_h,
+                      t3d_stream stream);
+
+/* Nearest neighbour (k=1) within radius: idx n_q int32 (-1 = none), d2 n_q f32. */
+int t3d_nearest_neighbor(t3d_ctx* ctx, const float* query, int64_t n_q,
+                         const float* ref, int64_t n_ref, double radius,
+                         int32_t* out_idx, float* out_d2, t3d_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* K9 — PLY writers (host).  Replace save_reconstruction (d2r:673-703),       */
+/* _save_pointcloud (der:1283-1311), save_ply (dp:424-440).                   */
+/* ------------------------------------------------------------------------- */
+#define T3D_PLY_O3D_BINARY 0 /* Open3D write_point_cloud layout (R9)          */
+#define T3D_PLY_REF_ASCII 1  /* in-repo fallback layout (d2r:690-701)         */
+/* xyz_h: n*3 (f32|f64), rgb_h: n*3 u8 (nullable), nrm_h: n*3 f32|f64 same
+ * dtype as xyz (nullable, binary layout only). */
+int t3d_write_ply_h(const char* path, const void* xyz_h, int xyz_is_f64,
+                    const uint8_t* rgb_h, const void* nrm_h, int64_t n,
+                    int layout);
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic scenes: device-side generators used by bench.py and */
+/* the full-size property tests; tests compare them with the NumPy generator. */
+/* ------------------------------------------------------------------------- */
+/* scene 0 = tunnel T1 (cfg 2/3/5), scene 1 = relief plane S1 (cfg 1).
+ * Writes depth (H*W f32, metres) and bgr (H*W*3 u8) for frame `frame_index`
+ * and the world->camera pose [R|t] into T_cw_h (host, 12 doubles row-major 3x4,
+ * nullable).  depth==NULL: pose only. */
+int t3d_synth_frame(t3d_ctx* ctx, int scene, int frame_index, int H, int W,
+                    double fx, double fy, double cx, double cy, uint64_t seed,
+                    float noise_sigma, float* depth, uint8_t* bgr,
+                    double* T_cw_h, t3d_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T3D_H_ */

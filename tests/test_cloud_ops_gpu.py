@@ -1,0 +1,199 @@
+"""K2 voxel downsample, K3 outlier removal, K7 normals, K8 ICP, K9 PLY — CUDA vs oracle.
+(Open3D semantics restated in oracle/t3d_oracle.c; parity unpinned by the reference.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from textureless_3d_reconstruction_b200 import synthetic as S
+
+
+def cloud(n_frames=3, H=240, W=136, sub=1):
+    """fused T1 cloud through the oracle's back-projection (f32 xyz, u8 rgb)."""
+    from oracle import capi
+    it = S.scaled_intrinsics(H, W)
+    P, C = [], []
+    for i in range(n_frames):
+        d, c, T = S.synth_frame(0, i, H, W, it["fx"], it["fy"], it["cx"], it["cy"], noise_sigma=0.002)
+        c = (np.arange(H * W * 3, dtype=np.uint32).reshape(H, W, 3) * 2654435761 >> 13).astype(np.uint8)
+        p, col = capi.backproject(d, c, it["fx"], it["fy"], it["cx"], it["cy"], max_depth=5.0,
+                                  pose=(T[:, :3].copy(), T[:, 3:4].copy()), subsample=sub)
+        P.append(p), C.append(col)
+    return np.vstack(P), np.vstack(C)
+
+
+def sort_by_idx(idx, *arrs):
+    order = np.lexsort((idx[:, 2], idx[:, 1], idx[:, 0]))
+    return (idx[order],) + tuple(a[order] for a in arrs)
+
+
+@pytest.mark.parametrize("voxel", [0.005, 0.02, 0.1])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_voxel_downsample_vs_oracle(ctx, oracle, voxel, dtype):
+    import torch
+    pts, cols = cloud()
+    o = oracle.voxel_downsample(pts.astype(np.float64), cols, voxel)
+    g = ctx.voxel_downsample(torch.from_numpy(pts.astype(dtype)).cuda(), torch.from_numpy(cols).cuda(), voxel)
+    assert g["m"] == len(o["points"])                                   # post-downsample count bit-exact
+    gi = g["idx"].cpu().numpy()
+    assert np.array_equal(gi, o["idx"])                                 # sorted output == oracle's key order
+    assert np.array_equal(g["count"].cpu().numpy().astype(np.uint32), o["count"])
+    assert np.allclose(g["points"].cpu().numpy(), o["points"], rtol=1e-5, atol=1e-12)
+    assert np.array_equal(g["min_bound"], o["min_bound"])
+    gc, oc = g["colors"].cpu().numpy().astype(int), o["colors_u8"].astype(int)
+    assert np.abs(gc - oc).max() <= 1                                   # +-1 LSB
+    single = o["count"] == 1
+    assert np.array_equal(gc[single], oc[single])                       # single-point voxels exact
+    # unsorted mode: same set
+    g2 = ctx.voxel_downsample(torch.from_numpy(pts.astype(dtype)).cuda(), torch.from_numpy(cols).cuda(), voxel,
+                              sorted_output=False)
+    i2, p2 = sort_by_idx(g2["idx"].cpu().numpy(), g2["points"].cpu().numpy())
+    assert np.array_equal(i2, o["idx"]) and np.allclose(p2, o["points"], rtol=1e-5, atol=1e-12)
+
+
+def test_voxel_downsample_adversarial(ctx, oracle):
+    """points exactly on voxel faces, duplicates, large coordinates, single point, errors."""
+    import torch
+    from textureless_3d_reconstruction_b200._lib import T3DError
+    v = 0.01
+    rng = np.random.default_rng(3)
+    k = rng.integers(-2000, 2000, size=(5000, 3))
+    faces = (k * v).astype(np.float32)                         # on voxel faces (after f32 rounding)
+    dup = np.repeat(rng.uniform(-1, 1, size=(500, 3)).astype(np.float32), 7, axis=0)
+    far = (rng.uniform(-1, 1, size=(300, 3)) * 300.0).astype(np.float32)
+    pts = np.vstack([faces, dup, far])
+    cols = rng.integers(0, 256, size=(len(pts), 3), dtype=np.uint8)
+    o = oracle.voxel_downsample(pts.astype(np.float64), cols, v)
+    g = ctx.voxel_downsample(torch.from_numpy(pts).cuda(), torch.from_numpy(cols).cuda(), v)
+    assert g["m"] == len(o["points"])
+    assert np.array_equal(g["idx"].cpu().numpy(), o["idx"])
+    assert np.array_equal(g["count"].cpu().numpy().astype(np.uint32), o["count"])
+    one = ctx.voxel_downsample(torch.tensor([[1.0, 2.0, 3.0]], device="cuda"), None, 0.5)
+    assert one["m"] == 1 and np.allclose(one["points"].cpu().numpy(), [[1, 2, 3]])
+    with pytest.raises(T3DError):
+        ctx.voxel_downsample(torch.from_numpy(pts).cuda(), None, 0.0)
+    with pytest.raises(T3DError):
+        ctx.voxel_downsample(torch.from_numpy(pts).cuda(), None, 1e-9)  # > 2^21 voxels per axis
+    empty = ctx.voxel_downsample(torch.empty((0, 3), device="cuda"), None, 0.1)
+    assert empty["m"] == 0
+
+
+def test_statistical_outlier_vs_oracle(ctx, oracle):
+    import torch
+    pts, cols = cloud(2)
+    ds = oracle.voxel_downsample(pts.astype(np.float64), cols, 0.02)["points"]
+    rng = np.random.default_rng(0)
+    ds = np.vstack([ds, rng.uniform(-3, 3, size=(200, 3)) + [0, 0, 3], ds[:5]])   # outliers + exact duplicates
+    keep_o, mean_o, st_o = oracle.statistical_outlier(ds, 20, 2.0)
+    keep, mean, st, kept = ctx.statistical_outlier(torch.from_numpy(ds).cuda(), 20, 2.0)
+    mean = mean.cpu().numpy()
+    assert np.allclose(mean, mean_o, rtol=1e-12, atol=0)
+    assert np.allclose(st, st_o, rtol=1e-10)
+    boundary = np.abs(mean_o - st_o[2]) < 1e-9 * st_o[2]
+    k = keep.cpu().numpy().astype(bool)
+    assert np.array_equal(k[~boundary], keep_o[~boundary])
+    assert kept == int(k.sum()) and 0 < kept < len(ds)
+    out = ctx.compact_rows(torch.from_numpy(ds).cuda(), keep)
+    assert np.array_equal(out.cpu().numpy(), ds[k])                      # input order preserved (R3)
+    c8 = torch.from_numpy(rng.integers(0, 256, size=(len(ds), 3), dtype=np.uint8)).cuda()
+    assert np.array_equal(ctx.compact_rows(c8, keep).cpu().numpy(), c8.cpu().numpy()[k])
+
+
+def test_knn_grid_vs_bruteforce(ctx, oracle):
+    """the oracle's own grid KNN is checked against brute force, then the GPU mean distances."""
+    import torch
+    rng = np.random.default_rng(11)
+    pts = np.vstack([rng.normal(size=(3000, 3)), rng.normal(size=(50, 3)) * 20.0])
+    _, mean_o, _ = oracle.statistical_outlier(pts, 20, 2.0)
+    for i in rng.integers(0, len(pts), size=40):
+        d2, _ = oracle.knn_bruteforce(pts, pts[i], 20)
+        assert abs(np.sqrt(d2).mean() - mean_o[i]) <= 1e-12 * max(1.0, mean_o[i])
+    _, mean, _, _ = ctx.statistical_outlier(torch.from_numpy(pts).cuda(), 20, 2.0)
+    assert np.allclose(mean.cpu().numpy(), mean_o, rtol=1e-12)
+
+
+def test_normals_vs_oracle(ctx, oracle):
+    import torch
+    pts, cols = cloud(2)
+    ds = oracle.voxel_downsample(pts.astype(np.float64), cols, 0.02)["points"].astype(np.float32)
+    cam = np.array([0.0, 0.0, 0.0])
+    n_o = oracle.estimate_normals(ds, 30, orient_to=cam)
+    n_g = ctx.estimate_normals(torch.from_numpy(ds).cuda(), 30, orient_to=cam).cpu().numpy()
+    dots = np.abs((n_o * n_g).sum(1))
+    assert (dots >= 1 - 1e-6).mean() > 0.999 and dots.min() > 0.99       # |n.n_ref| >= 1-1e-6
+    # analytic check: a plane z = 0.3x + 0.1y has normal ~ (-0.3,-0.1,1)
+    g = np.stack(np.meshgrid(np.linspace(0, 1, 60), np.linspace(0, 1, 60)), -1).reshape(-1, 2)
+    plane = np.column_stack([g, 0.3 * g[:, 0] + 0.1 * g[:, 1]]).astype(np.float32)
+    n = ctx.estimate_normals(torch.from_numpy(plane).cuda(), 30).cpu().numpy()
+    ref = np.array([-0.3, -0.1, 1.0]) / np.linalg.norm([-0.3, -0.1, 1.0])
+    assert np.abs(np.abs(n @ ref) - 1).max() < 1e-5
+    tiny = ctx.estimate_normals(torch.tensor([[0., 0., 0.], [1., 0., 0.]], device="cuda"), 30).cpu().numpy()
+    assert np.array_equal(tiny, [[0, 0, 1], [0, 0, 1]])                  # < 3 neighbours -> (0,0,1)
+
+
+def test_icp_vs_oracle(ctx, oracle):
+    import torch
+    pts, cols = cloud(2)
+    tgt = oracle.voxel_downsample(pts.astype(np.float64), cols, 0.02)["points"].astype(np.float32)
+    nrm = oracle.estimate_normals(tgt, 30, orient_to=np.zeros(3))
+    a = 0.01
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    T_true = np.eye(4); T_true[:3, :3] = Rz; T_true[:3, 3] = [0.01, -0.008, 0.012]
+    src = ((tgt[::3] - T_true[:3, 3]) @ Rz).astype(np.float32)            # src = T_true^-1 tgt
+    o = oracle.icp_point_to_plane(src, tgt, nrm, 0.05, max_iter=30)
+    g = ctx.icp_point_to_plane(torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda(),
+                               torch.from_numpy(nrm).cuda(), 0.05, max_iter=30)
+    # first linearisation: 27 normal-equation terms
+    a27, sd2, cnt = ctx.icp_linearize(torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda(),
+                                      torch.from_numpy(nrm).cuda(), 0.05, np.eye(4))
+    assert cnt == o["acc_first"][28]                                      # correspondence count exact
+    assert np.allclose(a27, o["acc_first"][:27], rtol=1e-9, atol=1e-12)
+    assert np.isclose(sd2, o["acc_first"][27], rtol=1e-9)
+    assert g.iterations == o["iterations"]
+    dT = g.transformation @ np.linalg.inv(o["T"])
+    ang = np.arccos(np.clip((np.trace(dT[:3, :3]) - 1) / 2, -1, 1))
+    assert ang <= 1e-4 and np.linalg.norm(dT[:3, 3]) <= 1e-4              # north_star ICP tolerance
+    assert abs(g.fitness - o["fitness"]) < 1e-9 and abs(g.inlier_rmse - o["inlier_rmse"]) < 1e-9
+    # and it actually recovers the motion
+    dT = g.transformation @ np.linalg.inv(T_true)
+    assert np.linalg.norm(dT[:3, 3]) < 2e-3
+    idx, d2 = ctx.nearest_neighbor(torch.from_numpy(src[:500]).cuda(), torch.from_numpy(tgt).cuda(), 0.05)
+    oi, od = oracle.nearest_neighbor(src[:500], tgt, 0.05)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+
+
+def test_ply_writers(tmp_path):
+    """K9 host writers: reference ASCII layout byte-for-byte vs the reference's own file;
+    Open3D binary layout structurally (R9)."""
+    from conftest import GOLDEN
+    from textureless_3d_reconstruction_b200 import _lib
+    from textureless_3d_reconstruction_b200.runtime import write_ply
+    z = np.load(GOLDEN / "k9_ply_ascii.npz")
+    f = tmp_path / "a.ply"
+    write_ply(f, z["points"], z["colors"], layout=_lib.PLY_REF_ASCII)
+    assert f.read_bytes() == bytes(z["ply_f32"])
+    write_ply(f, z["points64"], z["colors"][:50], layout=_lib.PLY_REF_ASCII)
+    assert f.read_bytes() == bytes(z["ply_f64"])
+    write_ply(f, z["points"], z["colors"], layout=_lib.PLY_O3D_BINARY)
+    raw = f.read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    assert head.decode().splitlines() == [
+        "ply", "format binary_little_endian 1.0", "comment Created by Open3D", "element vertex 200",
+        "property double x", "property double y", "property double z",
+        "property uchar red", "property uchar green", "property uchar blue"]
+    rec = np.frombuffer(body, dtype=np.dtype([("p", "<f8", 3), ("c", "u1", 3)]))
+    assert np.array_equal(rec["p"], z["points"].astype(np.float64)) and np.array_equal(rec["c"], z["colors"])
+
+
+def test_device_synth_matches_numpy_twin(ctx):
+    H, W = 240, 136
+    it = S.scaled_intrinsics(H, W)
+    for scene in (0, 1):
+        d, c, T = ctx.synth_frame(scene, 5, H, W, it["fx"], it["fy"], it["cx"], it["cy"], noise_sigma=0.002)
+        dn, cn, Tn = S.synth_frame(scene, 5, H, W, it["fx"], it["fy"], it["cx"], it["cy"], noise_sigma=0.002)
+        d = d.cpu().numpy()
+        assert np.allclose(T, Tn, atol=1e-12)
+        assert np.array_equal(c.cpu().numpy(), cn)
+        assert np.array_equal(np.isnan(d), np.isnan(dn)) and np.array_equal(np.isinf(d), np.isinf(dn))
+        fin = np.isfinite(dn)
+        assert np.abs(d[fin] - dn[fin]).max() < 2e-5                     # libm vs CUDA transcendentals

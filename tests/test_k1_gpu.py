@@ -1,0 +1,124 @@
+"""K1 parity: CUDA back-projection vs vectors produced by the unmodified reference
+(tests/golden/k1_backproject.npz) and vs the oracle at full 1080x1920 size."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCALES = {"pyfloat1": 1.0, "pyfloat": 1.37, "npf64": np.float64(1.37), "npf64_1": np.float64(1.0)}
+REL_TOL = 1e-5          # north_star: <= 1e-5 relative on point coordinates
+
+
+def poses_of(z):
+    return {"none": None, "identity": (np.eye(3), np.zeros((3, 1))),
+            "rotated": (z["pose_rotated_R"], z["pose_rotated_t"])}
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=REL_TOL, atol=1e-12)
+
+
+def test_golden_all_reference_copies(k1_golden, ctx):
+    from textureless_3d_reconstruction_b200 import depth_enhanced_reconstruction as der
+    from textureless_3d_reconstruction_b200 import depth_processor as dp
+    from textureless_3d_reconstruction_b200 import depth_to_reconstruction as d2r
+    z, meta = k1_golden
+    fx, fy, cx, cy = z["intrinsics"]
+    H, W = z["depth"].shape
+    poses = poses_of(z)
+    dense = d2r.DenseReconstructor(d2r.ReconstructionConfig(fx=fx, fy=fy, cx=cx, cy=cy))
+    gen = der.DensePointCloudGenerator(der.CameraIntrinsics(fx=fx, fy=fy, cx=cx, cy=cy, width=W, height=H))
+    exact = total = 0
+    for m in meta:
+        k = m["id"]
+        if m["kind"] in ("d2r", "d2r_zero"):
+            depth, color = (z["depth"], z["color"]) if m["kind"] == "d2r" else (
+                np.zeros((8, 12), np.float32), np.zeros((8, 12, 3), np.uint8))
+            pts, cols = dense.depth_to_pointcloud(depth, color, pose=poses[m["pose"]], scale=SCALES[m["scale"]],
+                                                  subsample=m["subsample"])
+            g_pts, g_cols = z[f"d2r_{k}_pts"], z[f"d2r_{k}_cols"]
+        elif m["kind"] in ("der", "der_b"):
+            depth, color = (z["depth"], z["color"]) if m["kind"] == "der" else (z["depth_b"], z["color_b"])
+            if m["depth"] == "f64":
+                depth = depth * np.float64(0.83)
+            pts, cols = gen.depth_to_pointcloud(depth, color, pose=poses[m["pose"]], subsample=m["subsample"])
+            g_pts, g_cols = z[f"der_{k}_pts"], z[f"der_{k}_cols"]
+        else:
+            g = dp.PointCloudGenerator(dp.CameraIntrinsics(fx=fx, fy=fy, cx=cx, cy=cy, width=W, height=H),
+                                       downsample_factor=m["downsample"])
+            pts, cols = g.generate(z["depth"], z["color"] if m["rgb"] else None, max_depth=20.0, min_depth=0.1)
+            g_pts = z[f"dp_{k}_pts"]
+            g_cols = z[f"dp_{k}_cols"] if m["rgb"] else None
+        assert pts.dtype == np.float32 and pts.shape == g_pts.shape, m   # mask + count bit-exact
+        assert close(pts, g_pts), m
+        if g_cols is None:
+            assert cols is None
+        else:
+            assert cols.dtype == g_cols.dtype and np.array_equal(cols, g_cols), m   # colours + order exact
+        exact += int((pts.view(np.uint32) == g_pts.view(np.uint32)).sum())
+        total += pts.size
+    assert exact / max(total, 1) > 0.999, exact / total
+
+
+@pytest.mark.parametrize("subsample", [1, 2, 4])
+def test_full_size_vs_oracle(ctx, oracle, subsample):
+    """cfg-1 frame (S1, W=1080 H=1920, NaN/inf/zero/border pixels) on device vs the C oracle."""
+    import torch
+    H, W = 1920, 1080
+    fx, fy, cx, cy = 1719.0, 1719.0, 540.0, 960.0
+    depth, bgr, T = ctx.synth_frame(1, 7, H, W, fx, fy, cx, cy)
+    pose = (T[:, :3].copy(), T[:, 3:4].copy())
+    xyz, rgb, n = ctx.backproject(depth, bgr, fx=fx, fy=fy, cx=cx, cy=cy, subsample=subsample, pose=pose)
+    n = int(n.item())
+    o_xyz, o_rgb = oracle.backproject(depth.cpu().numpy(), bgr.cpu().numpy(), fx, fy, cx, cy, pose=pose,
+                                      subsample=subsample)
+    assert n == len(o_xyz)
+    got = xyz[:n].cpu().numpy()
+    assert np.array_equal(rgb[:n].cpu().numpy(), o_rgb)
+    assert close(got, o_xyz)
+    assert (got.view(np.uint32) == o_xyz.view(np.uint32)).mean() > 0.9999
+    # size-independent property: every output point re-projects onto its own pixel
+    Pc = (pose[0] @ got.astype(np.float64).T + pose[1]).T
+    u = fx * Pc[:, 0] / Pc[:, 2] + cx
+    v = fy * Pc[:, 1] / Pc[:, 2] + cy
+    assert np.abs(u - np.round(u)).max() < 1e-2 and np.abs(v - np.round(v)).max() < 1e-2
+    lin = np.round(v).astype(np.int64) * W + np.round(u).astype(np.int64)
+    assert np.all(np.diff(lin) > 0)                     # row-major order, no duplicates
+
+
+def test_edge_shapes_and_conf_mask(ctx, oracle):
+    import torch
+    rng = np.random.default_rng(5)
+    for (H, W, s) in [(1, 1, 1), (5, 3, 2), (64, 32, 1), (33, 2049, 1), (7, 4100, 3), (300, 17, 7)]:
+        depth = rng.uniform(0.0, 3.0, size=(H, W)).astype(np.float32)
+        bgr = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        d, c = torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda()
+        xyz, rgb, n = ctx.backproject(d, c, fx=50.0, fy=51.0, cx=W / 2, cy=H / 2, subsample=s, min_depth=0.5,
+                                      max_depth=2.5)
+        n = int(n.item())
+        o_xyz, o_rgb = oracle.backproject(depth, bgr, 50.0, 51.0, W / 2, H / 2, min_depth=0.5, max_depth=2.5,
+                                          subsample=s)
+        assert n == len(o_xyz), (H, W, s)
+        assert np.array_equal(xyz[:n].cpu().numpy().view(np.uint32), o_xyz.view(np.uint32))
+        assert np.array_equal(rgb[:n].cpu().numpy(), o_rgb)
+    # confidence mask extension: identical to zeroing the depth of masked pixels
+    H, W = 40, 50
+    depth = rng.uniform(0.5, 3.0, size=(H, W)).astype(np.float32)
+    bgr = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    conf = (rng.uniform(size=(H, W)) > 0.3).astype(np.uint8)
+    xyz, rgb, n = ctx.backproject(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), fx=50., fy=50.,
+                                  cx=25., cy=20., conf_mask=torch.from_numpy(conf).cuda())
+    o_xyz, _ = oracle.backproject(np.where(conf > 0, depth, 0).astype(np.float32), bgr, 50., 50., 25., 20.)
+    assert int(n.item()) == len(o_xyz)
+    assert np.array_equal(xyz[: len(o_xyz)].cpu().numpy(), o_xyz)
+
+
+def test_capacity_and_argument_errors(ctx):
+    import torch
+    from textureless_3d_reconstruction_b200._lib import T3DError
+    d = torch.ones((8, 8), device="cuda")
+    small = torch.empty((3, 3), device="cuda")
+    with pytest.raises(T3DError):
+        ctx.backproject(d, None, fx=1., fy=1., cx=0., cy=0., out_xyz=small)
+    with pytest.raises(T3DError):
+        ctx.backproject(d, None, fx=1., fy=1., cx=0., cy=0., subsample=0)

@@ -1,0 +1,172 @@
+"""K4/K5/K6 parity vs the oracle (parity unpinned by the reference: no TSDF code there)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from textureless_3d_reconstruction_b200 import synthetic as S
+
+
+def frames(n, H, W, noise=0.002, scene=0, step=1):
+    it = S.scaled_intrinsics(H, W)
+    out = []
+    for i in range(n):
+        d, c, T = S.synth_frame(scene, i * step, H, W, it["fx"], it["fy"], it["cx"], it["cy"], noise_sigma=noise)
+        out.append((d, c, T))
+    return out, (it["fx"], it["fy"], it["cx"], it["cy"])
+
+
+def key_rows(a):
+    a = np.ascontiguousarray(a, np.int32)
+    return set(map(tuple, a.tolist()))
+
+
+def by_key(keys, *arrs):
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    return (keys[order],) + tuple(a[order] for a in arrs)
+
+
+@pytest.mark.parametrize("pixel_round", [0, 1])
+def test_touch_and_integrate_bit_exact(ctx, oracle, pixel_round):
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(5, H, W)
+    vol = TSDFVolume(0.01, 0.04, block_capacity=60000, pixel_round=pixel_round, ctx=ctx)
+    ov = oracle.TSDFVolume(0.01, 0.04, pixel_round)
+    for d, c, T in fr:
+        dd, cc = torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda()
+        gk = vol.touch(dd, K, T, 1.0, 5.0).cpu().numpy()
+        ok = ov.touch(d, K, T, 1.0, 5.0)
+        assert key_rows(gk) == key_rows(ok) and len(gk) == len(ok)      # R4: block key set bit-exact
+        vol.integrate(dd, cc, K, T, 1.0, 5.0)
+        ov.integrate(d, c, K, T, 1.0, 5.0)
+    assert vol.num_blocks == ov.num_blocks
+    assert vol.counters() == ov.counters()
+    gk, gt, gw, gc = [x.cpu().numpy() for x in vol.export_blocks()]
+    okk, ot, ow, oc = ov.export()
+    gk, gt, gw, gc = by_key(gk, gt, gw, gc)
+    okk, ot, ow, oc = by_key(okk, ot, ow, oc)
+    assert np.array_equal(gk, okk)
+    assert np.array_equal(gw, ow)                                        # occupancy + integer weights
+    assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32))        # tsdf bit-exact (<=1e-4 required)
+    assert np.array_equal(gc.view(np.uint32), oc.view(np.uint32))
+    # R6 surface points: same multiset
+    gp, gn, gcol = [x.cpu().numpy() for x in vol.extract_points(3.0)]
+    op, on, ocol = ov.extract_points(3.0)
+    assert len(gp) == len(op) and len(gp) > 1000
+    def rows(p, n, c):
+        a = np.concatenate([p.view(np.uint32), n.view(np.uint32), c.astype(np.uint32)], axis=1)
+        return a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(rows(gp, gn, gcol), rows(op, on, ocol))
+
+
+def test_batched_equals_sequential(ctx):
+    """Temporal blocking must not change a single bit: 1 x 7 frames == 7 x 1 frame."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(7, H, W)
+    ds = [torch.from_numpy(f[0]).cuda() for f in fr]
+    cs = [torch.from_numpy(f[1]).cuda() for f in fr]
+    Ts = [f[2] for f in fr]
+    a = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    b = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    a.integrate_batch(ds, cs, K, Ts, 1.0, 5.0)
+    for d, c, T in zip(ds, cs, Ts):
+        b.integrate(d, c, K, T, 1.0, 5.0)
+    assert a.counters() == b.counters() and a.num_blocks == b.num_blocks
+    ea = by_key(*[x.cpu().numpy() for x in a.export_blocks()])
+    eb = by_key(*[x.cpu().numpy() for x in b.export_blocks()])
+    for x, y in zip(ea, eb):
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
+                              y.view(np.uint32) if y.dtype == np.float32 else y)
+    # reset really forgets
+    a.reset()
+    assert a.num_blocks == 0 and a.counters()["voxel_updates"] == 0
+
+
+def test_u16_depth_no_color_and_merge(ctx, oracle):
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 160, 92
+    fr, K = frames(4, H, W, noise=0.0)
+    vol = TSDFVolume(0.02, 0.08, block_capacity=20000, ctx=ctx)
+    ov = oracle.TSDFVolume(0.02, 0.08)
+    for d, c, T in fr:
+        mm = np.clip(d * 1000.0, 0, 65535).astype(np.uint16)            # dp:919-921 depth PNG format
+        vol.integrate(torch.from_numpy(mm).cuda(), None, K, T, 1000.0, 5.0)
+        ov.integrate(mm, None, K, T, 1000.0, 5.0)
+    g = by_key(*[x.cpu().numpy() for x in vol.export_blocks()])
+    o = by_key(*ov.export())
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[2], o[2])
+    assert np.array_equal(g[1].view(np.uint32), o[1].view(np.uint32))
+    # merge of two half-volumes == weights add, tsdf = weighted mean
+    A = TSDFVolume(0.02, 0.08, block_capacity=20000, ctx=ctx)
+    B = TSDFVolume(0.02, 0.08, block_capacity=20000, ctx=ctx)
+    for i, (d, c, T) in enumerate(fr):
+        (A if i % 2 == 0 else B).integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    full = TSDFVolume(0.02, 0.08, block_capacity=20000, ctx=ctx)
+    for d, c, T in fr:
+        full.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    kb, tb, wb, cb = B.export_blocks()
+    A.merge_blocks(kb.contiguous(), tb.contiguous(), wb.contiguous(), cb.contiguous())
+    m = by_key(*[x.cpu().numpy() for x in A.export_blocks()])
+    f = by_key(*[x.cpu().numpy() for x in full.export_blocks()])
+    assert np.array_equal(m[0], f[0]) and np.array_equal(m[2], f[2])     # keys + weights exact
+    assert np.abs(m[1] - f[1]).max() <= 1e-4                             # north_star tsdf tolerance
+    assert np.abs(m[3] - f[3]).max() <= 1e-2
+
+
+def test_capacity_overflow_is_reported(ctx):
+    import torch
+    from textureless_3d_reconstruction_b200._lib import T3DError
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    fr, K = frames(1, 160, 92, noise=0.0)
+    vol = TSDFVolume(0.01, 0.04, block_capacity=16, ctx=ctx)
+    vol.integrate(torch.from_numpy(fr[0][0]).cuda(), None, K, fr[0][2], 1.0, 5.0)
+    with pytest.raises(T3DError):
+        _ = vol.num_blocks
+
+
+def test_full_size_properties(ctx):
+    """cfg-2 sized frames (1080x1920, device-generated): size-independent invariants."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 1920, 1080
+    K = (1719.0, 1719.0, 540.0, 960.0)
+    n = 6
+    fr = [ctx.synth_frame(0, i, H, W, *K, noise_sigma=0.002) for i in range(n)]
+    ds, cs, Ts = [f[0] for f in fr], [f[1] for f in fr], [f[2] for f in fr]
+    a = TSDFVolume(0.01, 0.04, block_capacity=120000, ctx=ctx)
+    a.integrate_batch(ds, cs, K, Ts, 1.0, 5.0)
+    cnt = a.counters()
+    keys, tsdf, w, rgb = a.export_blocks()
+    assert cnt["frames"] == n and cnt["voxel_updates"] > 1_000_000
+    assert int(w.sum().item()) == cnt["voxel_updates"]          # checksum: sum of weights == updates applied
+    assert float(w.max().item()) <= n and float(tsdf.abs().max().item()) <= 1.0
+    assert torch.isfinite(tsdf).all() and torch.isfinite(rgb).all()
+    assert len(key_rows(keys.cpu().numpy())) == a.num_blocks    # no duplicate blocks in the hash
+    touched = set()
+    for d, T in zip(ds, Ts):
+        touched |= key_rows(a.touch(d, K, T, 1.0, 5.0).cpu().numpy())
+    assert touched == key_rows(keys.cpu().numpy())
+    # grey albedo 128+-2 -> fused colours stay in [126,130] wherever weight > 0
+    m = w > 0
+    assert float(rgb[m].min().item()) >= 126.0 and float(rgb[m].max().item()) <= 130.0
+    # idempotent order: batch of 6 == 6 singles (bit-exact) at full size too
+    b = TSDFVolume(0.01, 0.04, block_capacity=120000, ctx=ctx)
+    for d, c, T in zip(ds, cs, Ts):
+        b.integrate(d, c, K, T, 1.0, 5.0)
+    assert b.counters() == cnt
+    kb, tb, wb, _ = b.export_blocks()
+    ka = by_key(keys.cpu().numpy(), tsdf.cpu().numpy(), w.cpu().numpy())
+    kbb = by_key(kb.cpu().numpy(), tb.cpu().numpy(), wb.cpu().numpy())
+    assert np.array_equal(ka[0], kbb[0]) and np.array_equal(ka[2], kbb[2])
+    assert np.array_equal(ka[1].view(np.uint32), kbb[1].view(np.uint32))
+    # surface points lie on the tunnel wall: radius within relief bounds +- a voxel
+    p, nrm, _ = a.extract_points(3.0)
+    r = torch.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2)
+    assert p.shape[0] > 50_000
+    assert float(r.min().item()) > 1.37 - 0.03 and float(r.max().item()) < 1.63 + 0.03
+    assert torch.allclose(nrm.norm(dim=1), torch.ones_like(r), atol=1e-4)

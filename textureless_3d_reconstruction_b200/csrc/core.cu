@@ -1,0 +1,77 @@
+// core.cu — ctx lifetime, error string, launch accounting.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void t3d_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* t3d_last_error(void) { return g_err; }
+extern "C" int t3d_version(void) { return T3D_VERSION; }
+
+extern "C" t3d_ctx* t3d_create(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    t3d_set_error("t3d_create: no CUDA device (%s); libt3d has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    return nullptr;
+  }
+  if (device < 0 || device >= count) {
+    t3d_set_error("t3d_create: device %d out of range [0,%d)", device, count);
+    return nullptr;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    t3d_set_error("t3d_create: cudaSetDevice(%d) -> %s", device,
+                  cudaGetErrorString(e));
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    t3d_set_error("t3d_create: cudaGetDeviceProperties -> %s",
+                  cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (prop.major != 10) {
+    t3d_set_error(
+        "t3d_create: device is sm_%d%d; libt3d is built for sm_100a (B200) only",
+        prop.major, prop.minor);
+    return nullptr;
+  }
+  t3d_ctx* ctx = new t3d_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->pinned_bytes = 1 << 16;
+  e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes);
+  if (e != cudaSuccess) {
+    t3d_set_error("t3d_create: cudaMallocHost -> %s", cudaGetErrorString(e));
+    delete ctx;
+    return nullptr;
+  }
+  return ctx;
+}
+
+extern "C" void t3d_destroy(t3d_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (ProjTable& t : ctx->proj) {
+    cudaFree(t.xf);
+    cudaFree(t.yf);
+  }
+  ctx->scan_state.release();
+  for (DevBuf& b : ctx->scratch) b.release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+}
+
+extern "C" int64_t t3d_launch_count(const t3d_ctx* ctx) {
+  return ctx ? ctx->launches : 0;
+}

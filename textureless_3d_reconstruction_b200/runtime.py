@@ -1,0 +1,397 @@
+"""Device-tensor API over the C ABI: torch owns the memory and the streams,
+libt3d.so does the work.  Every method takes/returns CUDA torch tensors and is
+the layer the drop-in classes (depth_to_reconstruction.py etc.) and bench.py
+call.  No method here computes anything on the CPU or with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import BackprojectParams, FrameView, IcpResult, TsdfParams, check
+
+_contexts: dict[int, "Context"] = {}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def get_context(device: int | None = None) -> "Context":
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "textureless_3d_reconstruction_b200 needs a CUDA device (B200, sm_100a); "
+            "there is no CPU fallback.")
+    if device is None:
+        device = torch.cuda.current_device()
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _contexts[device] = ctx
+    return ctx
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class IcpOutput:
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    iterations: int
+    converged: bool
+    correspondences: int
+
+
+class Context:
+    """One libt3d context on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device; libt3d has no CPU fallback")
+        torch.cuda.init()
+        self.device = torch.device("cuda", device)
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = self.lib.t3d_create(device)
+        if not h:
+            raise _lib.T3DError(_lib.T3D_E_CUDA, _lib.last_error())
+        self.handle = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.t3d_destroy(self.handle)
+            self.handle = None
+
+    def launch_count(self) -> int:
+        return int(self.lib.t3d_launch_count(self.handle))
+
+    # ------------------------------------------------------------------ K1
+    def backproject(self, depth, bgr, *, fx, fy, cx, cy, subsample=1, scale=1.0, scale_is_f64=False,
+                    min_depth=0.1, max_depth=50.0, pose=None, rgb_out_f32=False, conf_mask=None,
+                    out_xyz=None, out_rgb=None, out_n=None):
+        """depth: (H,W) f32|f64 CUDA tensor, bgr: (H,W,3) u8 CUDA tensor or None.
+        Returns (xyz[cap,3] f32, rgb[cap,3] u8|f32 or None, n int64[1]) — all on device;
+        only the first n rows are valid."""
+        torch = _torch()
+        H, W = depth.shape
+        assert depth.is_cuda and depth.is_contiguous()
+        assert depth.dtype in (torch.float32, torch.float64)
+        p = BackprojectParams()
+        p.H, p.W, p.subsample = H, W, int(subsample)
+        p.depth_is_f64 = int(depth.dtype == torch.float64)
+        p.scale_is_f64 = int(bool(scale_is_f64))
+        p.has_pose = int(pose is not None)
+        p.rgb_out_f32 = int(bool(rgb_out_f32))
+        p.has_color = int(bgr is not None)
+        p.fx, p.fy, p.cx, p.cy = float(fx), float(fy), float(cx), float(cy)
+        p.scale, p.min_depth, p.max_depth = float(scale), float(min_depth), float(max_depth)
+        if pose is not None:
+            R = np.ascontiguousarray(pose[0], np.float64).reshape(9)
+            t = np.ascontiguousarray(pose[1], np.float64).reshape(3)
+            p.R[:] = R.tolist()
+            p.t[:] = t.tolist()
+        s = int(subsample)
+        cap = (-(-H // s)) * (-(-W // s)) if s >= 1 else 0
+        if out_xyz is None:
+            out_xyz = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=depth.device)
+        if bgr is not None and out_rgb is None:
+            out_rgb = torch.empty((max(cap, 1), 3), dtype=torch.float32 if rgb_out_f32 else torch.uint8,
+                                  device=depth.device)
+        if out_n is None:
+            out_n = torch.zeros(1, dtype=torch.int64, device=depth.device)
+        if bgr is not None:
+            assert bgr.is_cuda and bgr.is_contiguous() and bgr.dtype == torch.uint8
+        check(self.lib.t3d_backproject(self.handle, _ptr(depth), _ptr(bgr), _ptr(conf_mask), C.byref(p),
+                                       _ptr(out_xyz), _ptr(out_rgb), out_xyz.shape[0], _ptr(out_n), _stream()))
+        return out_xyz, out_rgb, out_n
+
+    # ------------------------------------------------------------------ K2
+    def voxel_downsample(self, xyz, rgb, voxel_size, *, min_bound=None, sorted_output=True,
+                         want_idx=True, capacity=None):
+        """xyz: (N,3) f32|f64, rgb: (N,3) u8 or None.  Returns a dict of device tensors
+        (points f64, colors u8, rgb_sum u32, count u32, idx i32) trimmed to M rows."""
+        torch = _torch()
+        n = xyz.shape[0]
+        dev = xyz.device
+        assert xyz.is_contiguous()
+        cap = int(capacity) if capacity is not None else n
+        o_xyz = torch.empty((max(cap, 1), 3), dtype=torch.float64, device=dev)
+        o_rgb = torch.empty((max(cap, 1), 3), dtype=torch.uint8, device=dev) if rgb is not None else None
+        o_sum = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if rgb is not None else None
+        o_cnt = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        o_idx = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if want_idx else None
+        o_m = torch.zeros(1, dtype=torch.int64, device=dev)
+        mb_in = None if min_bound is None else np.ascontiguousarray(min_bound, np.float64)
+        mb_out = np.zeros(3, np.float64)
+        check(self.lib.t3d_voxel_downsample(
+            self.handle, _ptr(xyz), int(xyz.dtype == torch.float64), _ptr(rgb), n, float(voxel_size),
+            _np_ptr(mb_in), int(bool(sorted_output)), _ptr(o_xyz), _ptr(o_rgb), _ptr(o_sum), _ptr(o_cnt),
+            _ptr(o_idx), cap, _ptr(o_m), _np_ptr(mb_out), _stream()))
+        m = int(o_m.item())
+        return dict(points=o_xyz[:m], colors=None if o_rgb is None else o_rgb[:m],
+                    rgb_sum=None if o_sum is None else o_sum[:m], count=o_cnt[:m],
+                    idx=None if o_idx is None else o_idx[:m], min_bound=mb_out, m=m)
+
+    def bounds(self, xyz):
+        torch = _torch()
+        mn, mx = np.zeros(3), np.zeros(3)
+        check(self.lib.t3d_bounds(self.handle, _ptr(xyz), int(xyz.dtype == torch.float64), xyz.shape[0],
+                                  _np_ptr(mn), _np_ptr(mx), _stream()))
+        return mn, mx
+
+    # ------------------------------------------------------------------ K3
+    def statistical_outlier(self, xyz, nb_neighbors=20, std_ratio=2.0):
+        """xyz: (N,3) f64.  Returns (keep u8[N], mean_dist f64[N], (mu, sigma, thr), kept)."""
+        torch = _torch()
+        n = xyz.shape[0]
+        assert xyz.dtype == torch.float64 and xyz.is_contiguous()
+        keep = torch.zeros(max(n, 1), dtype=torch.uint8, device=xyz.device)
+        mean = torch.empty(max(n, 1), dtype=torch.float64, device=xyz.device)
+        kept = torch.zeros(1, dtype=torch.int64, device=xyz.device)
+        stats = np.zeros(3, np.float64)
+        check(self.lib.t3d_statistical_outlier(self.handle, _ptr(xyz), n, int(nb_neighbors), float(std_ratio),
+                                               _ptr(mean), _ptr(keep), _ptr(kept), _np_ptr(stats), _stream()))
+        return keep[:n], mean[:n], tuple(stats), int(kept.item())
+
+    def compact_rows(self, rows, keep):
+        torch = _torch()
+        n = rows.shape[0]
+        assert rows.is_contiguous() and keep.dtype == torch.uint8
+        row_bytes = rows.element_size() * (rows.numel() // max(n, 1)) if n else rows.element_size()
+        out = torch.empty_like(rows)
+        out_n = torch.zeros(1, dtype=torch.int64, device=rows.device)
+        check(self.lib.t3d_compact_rows(self.handle, _ptr(rows), n, row_bytes, _ptr(keep), _ptr(out), _ptr(out_n),
+                                        _stream()))
+        return out[: int(out_n.item())]
+
+    # ------------------------------------------------------------------ K7
+    def estimate_normals(self, xyz, knn=30, orient_to=None):
+        torch = _torch()
+        assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+        nrm = torch.empty_like(xyz)
+        o = None if orient_to is None else np.ascontiguousarray(orient_to, np.float64)
+        check(self.lib.t3d_estimate_normals(self.handle, _ptr(xyz), xyz.shape[0], int(knn), _np_ptr(o), _ptr(nrm),
+                                            _stream()))
+        return nrm
+
+    # ------------------------------------------------------------------ K8
+    def icp_point_to_plane(self, src, tgt, tgt_nrm, max_corr_dist, init=None, max_iter=30,
+                           relative_fitness=1e-6, relative_rmse=1e-6) -> IcpOutput:
+        torch = _torch()
+        for t in (src, tgt, tgt_nrm):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        T0 = None if init is None else np.ascontiguousarray(init, np.float64).reshape(16)
+        res = IcpResult()
+        check(self.lib.t3d_icp_point_to_plane(self.handle, _ptr(src), src.shape[0], _ptr(tgt), _ptr(tgt_nrm),
+                                              tgt.shape[0], float(max_corr_dist), _np_ptr(T0), int(max_iter),
+                                              float(relative_fitness), float(relative_rmse), C.byref(res),
+                                              _stream()))
+        return IcpOutput(np.array(res.T[:], np.float64).reshape(4, 4), res.fitness, res.inlier_rmse,
+                         res.iterations, bool(res.converged), int(res.correspondences))
+
+    def icp_linearize(self, src, tgt, tgt_nrm, max_corr_dist, T):
+        """One linearisation: returns (acc27, sum_d2, count) as host values."""
+        Th = np.ascontiguousarray(T, np.float64).reshape(16)
+        a27 = np.zeros(27, np.float64)
+        st = np.zeros(2, np.float64)
+        check(self.lib.t3d_icp_linearize(self.handle, _ptr(src), src.shape[0], _ptr(tgt), _ptr(tgt_nrm),
+                                         tgt.shape[0], float(max_corr_dist), _np_ptr(Th), _np_ptr(a27),
+                                         _np_ptr(st), _stream()))
+        return a27, float(st[0]), float(st[1])
+
+    def nearest_neighbor(self, query, ref, radius):
+        torch = _torch()
+        idx = torch.empty(max(query.shape[0], 1), dtype=torch.int32, device=query.device)
+        d2 = torch.empty(max(query.shape[0], 1), dtype=torch.float32, device=query.device)
+        check(self.lib.t3d_nearest_neighbor(self.handle, _ptr(query), query.shape[0], _ptr(ref), ref.shape[0],
+                                            float(radius), _ptr(idx), _ptr(d2), _stream()))
+        return idx[: query.shape[0]], d2[: query.shape[0]]
+
+    # ------------------------------------------------------------------ synth
+    def synth_frame(self, scene, frame_index, H, W, fx, fy, cx, cy, seed=1234, noise_sigma=0.0,
+                    depth=None, bgr=None, pose_only=False):
+        """Returns (depth f32[H,W], bgr u8[H,W,3], T_cw f64[3,4])."""
+        torch = _torch()
+        T = np.zeros((3, 4), np.float64)
+        if not pose_only:
+            if depth is None:
+                depth = torch.empty((H, W), dtype=torch.float32, device=self.device)
+            if bgr is None:
+                bgr = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device)
+        check(self.lib.t3d_synth_frame(self.handle, int(scene), int(frame_index), H, W, float(fx), float(fy),
+                                       float(cx), float(cy), int(seed), float(noise_sigma),
+                                       None if pose_only else _ptr(depth), None if pose_only else _ptr(bgr),
+                                       _np_ptr(T), _stream()))
+        return depth, bgr, T
+
+
+class TSDFVolume:
+    """Voxel-block TSDF volume (K4/K5/K6) on one GPU."""
+
+    MAX_BATCH = 32
+
+    def __init__(self, voxel_size=0.01, sdf_trunc=0.04, block_capacity=200_000, pixel_round=0,
+                 ctx: Context | None = None):
+        self.ctx = ctx or get_context()
+        self.lib = self.ctx.lib
+        p = TsdfParams(float(voxel_size), float(sdf_trunc), 8, int(pixel_round), int(block_capacity), 0)
+        h = C.c_void_p()
+        check(self.lib.t3d_tsdf_create(self.ctx.handle, C.byref(p), C.byref(h)))
+        self.handle = h
+        self.voxel_size = float(voxel_size)
+        self.sdf_trunc = float(sdf_trunc)
+        self.block_capacity = int(block_capacity)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.t3d_tsdf_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def reset(self):
+        check(self.lib.t3d_tsdf_reset(self.handle, _stream()))
+
+    @staticmethod
+    def make_frame_views(depths, bgrs, Ks, T_cws):
+        """Build the host-side frame descriptor array once (bench: outside the timed loop)."""
+        n = len(depths)
+        arr = (FrameView * n)()
+        for i in range(n):
+            arr[i].depth = depths[i].data_ptr()
+            arr[i].bgr = bgrs[i].data_ptr() if bgrs is not None and bgrs[i] is not None else None
+            K = np.asarray(Ks[i] if isinstance(Ks, (list, tuple)) else Ks, np.float32).reshape(4)
+            T = np.asarray(T_cws[i], np.float64)[:3, :4].astype(np.float32).reshape(12)
+            arr[i].K[:] = K.tolist()
+            arr[i].T_cw[:] = T.tolist()
+        return arr
+
+    def integrate_views(self, views, start, count, H, W, depth_is_u16=False, depth_scale=1.0, depth_max=5.0):
+        """Fuse views[start:start+count] (count <= 32) in one temporally blocked pass."""
+        sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
+        check(self.lib.t3d_tsdf_integrate(self.handle, sub, int(count), int(H), int(W), int(depth_is_u16),
+                                          float(depth_scale), float(depth_max), _stream()))
+
+    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0):
+        """Fuse one frame.  depth: (H,W) f32|u16 CUDA tensor; bgr: (H,W,3) u8 or None;
+        K=(fx,fy,cx,cy); T_cw: world->camera 4x4 or 3x4."""
+        torch = _torch()
+        H, W = depth.shape
+        views = self.make_frame_views([depth], [bgr], [K], [T_cw])
+        self.integrate_views(views, 0, 1, H, W, depth.dtype in (torch.uint16, torch.int16), depth_scale, depth_max)
+
+    def integrate_batch(self, depths, bgrs, K, T_cws, depth_scale=1.0, depth_max=5.0):
+        torch = _torch()
+        H, W = depths[0].shape
+        n = len(depths)
+        views = self.make_frame_views(depths, bgrs, [K] * n, T_cws)
+        for s in range(0, n, self.MAX_BATCH):
+            self.integrate_views(views, s, min(self.MAX_BATCH, n - s), H, W,
+                                 depths[0].dtype in (torch.uint16, torch.int16), depth_scale, depth_max)
+
+    def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0):
+        """K4 only: unique block keys (int32 [n,3], device) touched by one frame."""
+        torch = _torch()
+        H, W = depth.shape
+        views = self.make_frame_views([depth], None, [K], [T_cw])
+        cap = (H // 4) * (W // 4) * 4 + 1
+        keys = torch.empty((cap, 3), dtype=torch.int32, device=depth.device)
+        n = torch.zeros(1, dtype=torch.int64, device=depth.device)
+        check(self.lib.t3d_tsdf_touch(self.handle, views, H, W, int(depth.dtype in (torch.uint16, torch.int16)),
+                                      float(depth_scale), float(depth_max), _ptr(keys), cap, _ptr(n), _stream()))
+        return keys[: int(n.item())]
+
+    @property
+    def num_blocks(self) -> int:
+        n = int(self.lib.t3d_tsdf_num_blocks(self.handle, _stream()))
+        if n < 0:
+            raise _lib.T3DError(n, _lib.last_error())
+        return n
+
+    def counters(self, detailed=False) -> dict:
+        c = np.zeros(5, np.int64)
+        check(self.lib.t3d_tsdf_counters(self.handle, _np_ptr(c), _stream()))
+        out = dict(voxel_updates=int(c[0]), block_frames=int(c[1]), frames=int(c[2]))
+        if detailed:
+            out.update(voxels_changed_per_visit=int(c[3]), block_visits=int(c[4]))
+        return out
+
+    def set_profiling(self, enable=True):
+        check(self.lib.t3d_tsdf_set_profiling(self.handle, int(bool(enable))))
+
+    def get_profile(self) -> dict:
+        p = np.zeros(3, np.float64)
+        check(self.lib.t3d_tsdf_get_profile(self.handle, _np_ptr(p), _stream()))
+        return dict(touch_ms=float(p[0]), integrate_ms=float(p[1]), calls=int(p[2]))
+
+    def export_blocks(self):
+        torch = _torch()
+        nb = self.num_blocks
+        dev = self.ctx.device
+        keys = torch.empty((max(nb, 1), 3), dtype=torch.int32, device=dev)
+        tsdf = torch.empty((max(nb, 1), 512), dtype=torch.float32, device=dev)
+        w = torch.empty((max(nb, 1), 512), dtype=torch.float32, device=dev)
+        rgb = torch.empty((max(nb, 1), 512, 3), dtype=torch.float32, device=dev)
+        out_b = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.lib.t3d_tsdf_export_blocks(self.handle, _ptr(keys), _ptr(tsdf), _ptr(w), _ptr(rgb), max(nb, 1),
+                                              _ptr(out_b), _stream()))
+        return keys[:nb], tsdf[:nb], w[:nb], rgb[:nb]
+
+    def merge_blocks(self, keys, tsdf, weight, rgb):
+        check(self.lib.t3d_tsdf_merge_blocks(self.handle, _ptr(keys), _ptr(tsdf), _ptr(weight), _ptr(rgb),
+                                             keys.shape[0], _stream()))
+
+    def extract_points(self, weight_threshold=3.0, with_normals=True, with_colors=True, capacity=None):
+        torch = _torch()
+        dev = self.ctx.device
+        cap = int(capacity) if capacity else max(self.num_blocks * 96, 1024)
+        while True:
+            xyz = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            nrm = torch.empty((cap, 3), dtype=torch.float32, device=dev) if with_normals else None
+            rgb = torch.empty((cap, 3), dtype=torch.uint8, device=dev) if with_colors else None
+            n = torch.zeros(1, dtype=torch.int64, device=dev)
+            check(self.lib.t3d_tsdf_extract_points(self.handle, float(weight_threshold), _ptr(xyz), _ptr(nrm),
+                                                   _ptr(rgb), cap, _ptr(n), _stream()))
+            cnt = int(n.item())
+            if cnt <= cap:
+                return xyz[:cnt], (nrm[:cnt] if nrm is not None else None), (rgb[:cnt] if rgb is not None else None)
+            cap = cnt
+
+
+def write_ply(path, points, colors=None, normals=None, layout=_lib.PLY_O3D_BINARY):
+    """Host-side PLY writer through the C ABI (K9).  points: (N,3) f32|f64 NumPy."""
+    lib = _lib.load()
+    pts = np.ascontiguousarray(points)
+    if pts.dtype not in (np.float32, np.float64):
+        pts = pts.astype(np.float64)
+    n = len(pts)
+    cols = None
+    if colors is not None:
+        cols = np.ascontiguousarray(colors)
+        if cols.dtype != np.uint8:
+            cols = cols.astype(np.uint8)
+    nr = None if normals is None else np.ascontiguousarray(normals, pts.dtype)
+    check(lib.t3d_write_ply_h(str(path).encode(), _np_ptr(pts), int(pts.dtype == np.float64), _np_ptr(cols),
+                              _np_ptr(nr), n, int(layout)))
