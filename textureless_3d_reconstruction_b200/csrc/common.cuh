@@ -110,7 +110,11 @@ inline cudaStream_t as_stream(t3d_stream s) {
 // ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lane_id() {  // hardware lane (valid for 2-D blocks too)
+  unsigned l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
