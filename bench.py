@@ -278,7 +278,7 @@ def run_ours(args):
     }
 
     # ---- e2e: host buffers -> H2D -> fuse -> D2H result, through the public API
-    e2e = run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist if world > 1 else None)
+    e2e = None if args.no_e2e else run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist if world > 1 else None)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -392,6 +392,7 @@ def main():
     ap.add_argument("--block-capacity", type=int, default=600_000)
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

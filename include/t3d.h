@@ -195,6 +195,13 @@ int t3d_tsdf_get_profile(t3d_tsdf* v, double* out3_h, t3d_stream stream);
 int t3d_tsdf_export_blocks(t3d_tsdf* v, int32_t* keys, float* tsdf,
                            float* weight, float* rgb, int64_t capacity,
                            int64_t* out_b, t3d_stream stream);
+/* Same, restricted to blocks whose key[axis] lies in [lo, hi) — the routing
+ * record of the multi-GPU path (ownership = z-slab of the block key, SURVEY
+ * §8e).  With all outputs NULL only the count is returned.  Synchronous. */
+int t3d_tsdf_export_blocks_range(t3d_tsdf* v, int axis, int32_t lo, int32_t hi,
+                                 int32_t* keys, float* tsdf, float* weight,
+                                 float* rgb, int64_t capacity, int64_t* out_b,
+                                 t3d_stream stream);
 /* Merge partial blocks into the volume (multi-GPU owner reduce):
  * w' = w_a + w_b, tsdf' = (w_a*tsdf_a + w_b*tsdf_b)/w', same for rgb. */
 int t3d_tsdf_merge_blocks(t3d_tsdf* v, const int32_t* keys, const float* tsdf,

@@ -19,7 +19,7 @@ _lib = None
 def build(force: bool = False) -> Path:
     src = _DIR / "t3d_oracle.c"
     if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
-        base = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+        base = ["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fno-fast-math", "-fPIC", "-shared",
                 "-fvisibility=hidden", "-o", str(_SO), str(src), "-lm"]
         r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], capture_output=True, text=True)
         if r.returncode != 0:  # no libgomp on this box: serial oracle

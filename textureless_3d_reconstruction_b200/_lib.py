@@ -78,6 +78,7 @@ _SIGS = {
     "t3d_tsdf_set_profiling": (_I, [_VP, _I]),
     "t3d_tsdf_get_profile": (_I, [_VP, _VP, _VP]),
     "t3d_tsdf_export_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
+    "t3d_tsdf_export_blocks_range": (_I, [_VP, _I, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),

@@ -1,0 +1,161 @@
+"""Multi-GPU sharding of the fused path: one process per GPU,
+torch.distributed (NCCL over NVLink/NVSwitch) only where data really has to move.
+
+* frame stream: rank r fuses frames [r*F, (r+1)*F) — no communication;
+* TSDF volume: split spatially by voxel-block ownership.  The camera advances along
+  +z, so ownership is the z-slab of the block key: owner(zb) = clamp(zb // slab_blocks).
+  After a rank has fused its frames, blocks it touched but does not own (the ~5 m of
+  look-ahead past its last camera) are routed to their owner with one variable-size
+  all_to_all and merged there as weighted means (running averages with unit weights
+  are mergeable: w = wa + wb, tsdf = (wa*ta + wb*tb) / w);
+* ICP: source points sharded, per-iteration all_reduce of the 29 normal-equation sums.
+
+Everything is written against `torch.distributed` collectives on whatever device the
+volume's tensors live on, so the same code runs under gloo on CPU tensors in the
+world_size-2 tests (tests/test_distributed_cpu.py) and under NCCL on the GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def block_owner_range(rank: int, world: int, slab_blocks: int):
+    """[lo, hi) of block z-keys owned by `rank`; the first/last slabs are open-ended."""
+    lo = -(1 << 30) if rank == 0 else rank * slab_blocks
+    hi = (1 << 30) if rank == world - 1 else (rank + 1) * slab_blocks
+    return lo, hi
+
+
+def owner_of(zb, world: int, slab_blocks: int):
+    """Vectorised owner of block z-keys (NumPy or torch integer array)."""
+    o = zb // slab_blocks
+    if hasattr(o, "clamp"):
+        return o.clamp(0, world - 1)
+    return np.clip(o, 0, world - 1)
+
+
+class BlockRouter:
+    """Routes non-owned TSDF blocks to their owner rank and merges them there.
+
+    `vol` needs: export_blocks_range(axis, lo, hi) -> (keys[n,3] i32, tsdf[n,512] f32,
+    weight[n,512] f32, rgb[n,512,3] f32) and merge_blocks(keys, tsdf, weight, rgb).
+    """
+
+    AXIS = 2
+
+    def __init__(self, vol, rank: int, world: int, slab_frames: int, frame_advance: float, block_size: float,
+                 group=None):
+        self.vol, self.rank, self.world, self.group = vol, rank, world, group
+        self.slab_blocks = max(1, int(round(slab_frames * frame_advance / block_size)))
+        self.last_sent = 0
+        self.last_received = 0
+
+    def route(self):
+        import torch
+        import torch.distributed as dist
+        world, rank = self.world, self.rank
+        if world == 1:
+            return 0
+        parts = []
+        for d in range(world):
+            if d == rank:
+                parts.append(None)
+                continue
+            lo, hi = block_owner_range(d, world, self.slab_blocks)
+            parts.append(self.vol.export_blocks_range(self.AXIS, lo, hi))
+        some = next(p for p in parts if p is not None)
+        dev = some[0].device
+        send_counts = torch.tensor([0 if p is None else p[0].shape[0] for p in parts], dtype=torch.int64, device=dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        self.last_sent, self.last_received = int(sum(sc)), int(sum(rc))
+        if self.last_sent == 0 and self.last_received == 0:
+            return 0
+
+        def exchange(idx, row_shape, dtype):
+            rows = [p[idx].reshape(p[idx].shape[0], -1) for p in parts if p is not None and p[idx].shape[0] > 0]
+            width = int(np.prod(row_shape))
+            send = torch.cat(rows) if rows else torch.empty((0, width), dtype=dtype, device=dev)
+            recv = torch.empty((sum(rc), width), dtype=dtype, device=dev)
+            dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc,
+                                   group=self.group)
+            return recv.reshape((sum(rc),) + tuple(row_shape))
+
+        keys = exchange(0, (3,), torch.int32)
+        tsdf = exchange(1, (512,), torch.float32)
+        weight = exchange(2, (512,), torch.float32)
+        rgb = exchange(3, (512, 3), torch.float32)
+        # a block can arrive from several ranks: merge one source rank at a time so that
+        # keys are unique inside each merge call
+        off = 0
+        for n in rc:
+            if n > 0:
+                self.vol.merge_blocks(keys[off:off + n].contiguous(), tsdf[off:off + n].contiguous(),
+                                      weight[off:off + n].contiguous(), rgb[off:off + n].contiguous())
+            off += n
+        return self.last_received
+
+
+def allreduce_normal_equations(acc27, sum_d2, count, device=None, group=None):
+    """ICP across ranks: every rank linearises its shard of source points
+    (Context.icp_linearize), then the 29 sums are all-reduced and every rank solves the
+    same 6x6 system."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(acc27) + [sum_d2, count], dtype=torch.float64, device=device)
+    dist.all_reduce(t, group=group)
+    out = t.cpu().numpy()
+    return out[:27], float(out[27]), float(out[28])
+
+
+def solve_icp_update(acc27):
+    """6x6 solve of the point-to-plane normal equations (host, f64) — same rule as the
+    library: |det| < 1e-6 or non-finite -> identity (R8)."""
+    A = np.zeros((6, 6))
+    q = 0
+    for a in range(6):
+        for b in range(a, 6):
+            A[a, b] = A[b, a] = acc27[q]
+            q += 1
+    b = -np.asarray(acc27[21:27], np.float64)
+    det = np.linalg.det(A)
+    U = np.eye(4)
+    if not np.isfinite(det) or abs(det) < 1e-6:
+        return U
+    x = np.linalg.solve(A, b)
+    if not np.all(np.isfinite(x)):
+        return U
+    ca, sa, cb, sb, cg, sg = np.cos(x[0]), np.sin(x[0]), np.cos(x[1]), np.sin(x[1]), np.cos(x[2]), np.sin(x[2])
+    U[:3, :3] = [[cg * cb, cg * sb * sa - sg * ca, cg * sb * ca + sg * sa],
+                 [sg * cb, sg * sb * sa + cg * ca, sg * sb * ca - cg * sa],
+                 [-sb, cb * sa, cb * ca]]
+    U[:3, 3] = x[3:]
+    return U
+
+
+def sharded_icp(ctx, src_shard, tgt, tgt_nrm, max_corr_dist, n_src_total, init=None, max_iter=30,
+                relative_fitness=1e-6, relative_rmse=1e-6, group=None):
+    """Point-to-plane ICP with the source cloud sharded across ranks.  Returns
+    (T, fitness, rmse, iterations) — identical on every rank."""
+    T = np.eye(4) if init is None else np.array(init, np.float64)
+
+    def lin(Tc):
+        a27, sd2, cnt = ctx.icp_linearize(src_shard, tgt, tgt_nrm, max_corr_dist, Tc)
+        return allreduce_normal_equations(a27, sd2, cnt, device=src_shard.device, group=group)
+
+    a27, sd2, cnt = lin(T)
+    fit = cnt / n_src_total
+    rmse = np.sqrt(sd2 / cnt) if cnt > 0 else 0.0
+    it = 0
+    while it < max_iter:
+        T = solve_icp_update(a27) @ T
+        a27, sd2, cnt = lin(T)
+        f2 = cnt / n_src_total
+        r2 = np.sqrt(sd2 / cnt) if cnt > 0 else 0.0
+        stop = abs(fit - f2) < relative_fitness and abs(rmse - r2) < relative_rmse
+        fit, rmse = f2, r2
+        it += 1
+        if stop:
+            break
+    return T, fit, rmse, it

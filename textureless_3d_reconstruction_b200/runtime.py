@@ -359,6 +359,28 @@ class TSDFVolume:
                                               _ptr(out_b), _stream()))
         return keys[:nb], tsdf[:nb], w[:nb], rgb[:nb]
 
+    def count_blocks_range(self, axis, lo, hi) -> int:
+        torch = _torch()
+        out_b = torch.zeros(1, dtype=torch.int64, device=self.ctx.device)
+        check(self.lib.t3d_tsdf_export_blocks_range(self.handle, int(axis), int(lo), int(hi), None, None, None, None,
+                                                    0, _ptr(out_b), _stream()))
+        return int(out_b.item())
+
+    def export_blocks_range(self, axis, lo, hi):
+        """Blocks with key[axis] in [lo, hi): (keys i32[n,3], tsdf[n,512], weight[n,512], rgb[n,512,3])."""
+        torch = _torch()
+        dev = self.ctx.device
+        n = self.count_blocks_range(axis, lo, hi)
+        keys = torch.empty((max(n, 1), 3), dtype=torch.int32, device=dev)
+        tsdf = torch.empty((max(n, 1), 512), dtype=torch.float32, device=dev)
+        w = torch.empty((max(n, 1), 512), dtype=torch.float32, device=dev)
+        rgb = torch.empty((max(n, 1), 512, 3), dtype=torch.float32, device=dev)
+        out_b = torch.zeros(1, dtype=torch.int64, device=dev)
+        if n > 0:
+            check(self.lib.t3d_tsdf_export_blocks_range(self.handle, int(axis), int(lo), int(hi), _ptr(keys), _ptr(tsdf),
+                                                        _ptr(w), _ptr(rgb), n, _ptr(out_b), _stream()))
+        return keys[:n], tsdf[:n], w[:n], rgb[:n]
+
     def merge_blocks(self, keys, tsdf, weight, rgb):
         check(self.lib.t3d_tsdf_merge_blocks(self.handle, _ptr(keys), _ptr(tsdf), _ptr(weight), _ptr(rgb),
                                              keys.shape[0], _stream()))
