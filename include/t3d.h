@@ -168,6 +168,16 @@ int t3d_tsdf_integrate(t3d_tsdf* v, const t3d_frame_view* frames_h,
                        int n_frames, int H, int W, int depth_is_u16,
                        float depth_scale, float depth_max, t3d_stream stream);
 
+/* Fuse a whole sequence with known poses (config 2): batches of `batch`
+ * (1..32) frames; K4 of batch b+1 runs on an internal stream underneath K5 of
+ * batch b.  Bit-identical to calling t3d_tsdf_integrate batch by batch.
+ * Work is ordered after prior work on `stream`, and `stream` ends ordered
+ * after all of it.  Asynchronous. */
+int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
+                                int n_frames, int batch, int H, int W,
+                                int depth_is_u16, float depth_scale,
+                                float depth_max, t3d_stream stream);
+
 /* K4 alone: unique block keys touched by one frame (R4).  out_keys: cap*3
  * int32; out_n device int64.  Does not modify the volume. */
 int t3d_tsdf_touch(t3d_tsdf* v, const t3d_frame_view* frame_h, int H, int W,

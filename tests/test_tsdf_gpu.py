@@ -81,6 +81,17 @@ def test_batched_equals_sequential(ctx):
     for x, y in zip(ea, eb):
         assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
                               y.view(np.uint32) if y.dtype == np.float32 else y)
+    # pipelined sequence (K4 of batch b+1 under K5 of batch b): 4 batches of 2,2,2,1 frames
+    c = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    views = c.make_frame_views(ds, cs, [K] * 7, Ts)
+    for rep in range(3):                       # repeat: exercises ping-pong parity carry-over + reset
+        c.reset()
+        c.integrate_sequence(views, 7, H, W, batch=2, depth_scale=1.0, depth_max=5.0)
+        assert c.counters() == b.counters() and c.num_blocks == b.num_blocks
+        ec = by_key(*[x.cpu().numpy() for x in c.export_blocks()])
+        for x, y in zip(ec, eb):
+            assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
+                                  y.view(np.uint32) if y.dtype == np.float32 else y)
     # reset really forgets
     a.reset()
     assert a.num_blocks == 0 and a.counters()["voxel_updates"] == 0

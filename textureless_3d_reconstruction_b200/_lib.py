@@ -72,6 +72,7 @@ _SIGS = {
     "t3d_tsdf_destroy": (None, [_VP]),
     "t3d_tsdf_reset": (_I, [_VP, _VP]),
     "t3d_tsdf_integrate": (_I, [_VP, C.POINTER(FrameView), _I, _I, _I, _I, _F, _F, _VP]),
+    "t3d_tsdf_integrate_sequence": (_I, [_VP, C.POINTER(FrameView), _I, _I, _I, _I, _I, _F, _F, _VP]),
     "t3d_tsdf_touch": (_I, [_VP, C.POINTER(FrameView), _I, _I, _I, _F, _F, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_num_blocks": (_I64, [_VP, _VP]),
     "t3d_tsdf_counters": (_I, [_VP, _VP, _VP]),

@@ -294,6 +294,14 @@ class TSDFVolume:
         check(self.lib.t3d_tsdf_integrate(self.handle, sub, int(count), int(H), int(W), int(depth_is_u16),
                                           float(depth_scale), float(depth_max), _stream()))
 
+    def integrate_sequence(self, views, n_frames, H, W, batch=32, depth_is_u16=False, depth_scale=1.0,
+                           depth_max=5.0, start=0):
+        """Fuse views[start:start+n_frames] in `batch`-frame passes with K4/K5 overlap."""
+        sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
+        check(self.lib.t3d_tsdf_integrate_sequence(self.handle, sub, int(n_frames), int(batch), int(H), int(W),
+                                                   int(depth_is_u16), float(depth_scale), float(depth_max),
+                                                   _stream()))
+
     def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0):
         """Fuse one frame.  depth: (H,W) f32|u16 CUDA tensor; bgr: (H,W,3) u8 or None;
         K=(fx,fy,cx,cy); T_cw: world->camera 4x4 or 3x4."""
@@ -307,9 +315,8 @@ class TSDFVolume:
         H, W = depths[0].shape
         n = len(depths)
         views = self.make_frame_views(depths, bgrs, [K] * n, T_cws)
-        for s in range(0, n, self.MAX_BATCH):
-            self.integrate_views(views, s, min(self.MAX_BATCH, n - s), H, W,
-                                 depths[0].dtype in (torch.uint16, torch.int16), depth_scale, depth_max)
+        self.integrate_sequence(views, n, H, W, self.MAX_BATCH, depths[0].dtype in (torch.uint16, torch.int16),
+                                depth_scale, depth_max)
 
     def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0):
         """K4 only: unique block keys (int32 [n,3], device) touched by one frame."""
