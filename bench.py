@@ -41,6 +41,17 @@ METRIC = "RGB-D frames fused/sec @1080x1920 (TSDF integration, cfg2)"
 UNIT = "frames/s"
 
 
+def load_traffic():
+    """DRAM bytes per K5 launch from the committed `ncu --set full` capture of this same
+    command (profiles/r1_k5_traffic.json, written by profiles/summarize_ncu.py traffic)."""
+    p = ROOT / "profiles" / "r1_k5_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["dram_bytes_per_launch"]), d
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -130,7 +141,8 @@ def run_reference(args):
         ov = step()
     dt = time.perf_counter() - t0
     fps = args.steps * len(frames) / dt
-    sample = f"first {len(frames)} of the 300 cfg2 frames per step (reset + touch + integrate), {cores} OpenMP threads"
+    sample = (f"frames 0..{len(frames) - 1} of the 300 cfg2 frames per step (new volume + touch + integrate), "
+              f"oracle/t3d_oracle.c, {cores} OpenMP threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -262,9 +274,12 @@ def run_ours(args):
     k5_ms_per_launch = prof["integrate_ms"] / max(prof["calls"], 1)
     k4_ms_per_launch = prof["touch_ms"] / max(prof["calls"], 1)
     achieved = (alg_bytes_step / calls_per_step) / (k5_ms_per_launch * 1e-3) / 1e9
+    traffic, tinfo = load_traffic()
+    traffic_src = None if tinfo is None else tinfo.get("source")
     roofline = {
         "kernel": "integrate_kernel (K5)", "bound": "hbm", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_step / calls_per_step,
         "avg_launch_ms": k5_ms_per_launch, "launches_timed": prof["calls"],
         "temporal_blocking": {
@@ -381,7 +396,7 @@ def cpu_baseline(args, depth_all, bgr_all, poses):
         ov.integrate(d, c, KINTR, T, 1.0, DEPTH_MAX)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} of the 300 frames (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s",
+            "sample": f"frames 0..{n - 1} of the 300 cfg2 frames, one pass (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s wall",
             "voxel_updates": ov.counters()["voxel_updates"]}
 
 
@@ -394,7 +409,8 @@ def main():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--block-capacity", type=int, default=600_000)
-    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--cpu-frames", type=int, default=300,
+                    help="frames of the workload the CPU legs fuse per pass (300 = the whole cfg2 job, ~4 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     ap.add_argument("--serial-batches", action="store_true", help="(tuning) no K4/K5 overlap")
