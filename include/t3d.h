@@ -90,6 +90,27 @@ int t3d_backproject(t3d_ctx* ctx, const void* depth, const uint8_t* bgr,
                     float* out_xyz, void* out_rgb, int64_t capacity,
                     int64_t* out_n, t3d_stream stream);
 
+/* Batched K1: n_frames frames of identical geometry (H, W, subsample, intrinsics,
+ * scale, depth range, dtype flags taken from `p`; p->R / p->t are ignored, each
+ * frame carries its own pose) back-projected by ONE launch per 32 frames into ONE
+ * concatenated, frame-ordered output — the reference's per-frame loop followed by
+ * np.vstack (d2r:566-581,653-658 + d2r:401-402; der:1130-1145,1229-1237).
+ * frames_h: host array.  out_offsets: device int64[n_frames + 1]; frame i owns
+ * rows [out_offsets[i], out_offsets[i+1]).  capacity >= n_frames * ceil(H/s)*ceil(W/s).
+ * Asynchronous. */
+typedef struct t3d_backproject_frame {
+  const void* depth;        /* H*W f32|f64 (device)                               */
+  const uint8_t* bgr;       /* H*W*3 u8 BGR (device; NULL iff !p->has_color)      */
+  const uint8_t* conf_mask; /* nullable H*W u8                                    */
+  double R[9];              /* world->camera rotation, row-major (if p->has_pose) */
+  double t[3];
+} t3d_backproject_frame;
+
+int t3d_backproject_batch(t3d_ctx* ctx, const t3d_backproject_frame* frames_h,
+                          int n_frames, const t3d_backproject_params* p,
+                          float* out_xyz, void* out_rgb, int64_t capacity,
+                          int64_t* out_offsets, t3d_stream stream);
+
 /* ------------------------------------------------------------------------- */
 /* K2 — voxel-grid downsample.  Replaces Open3D                               */
 /* PointCloud.voxel_down_sample as called by merge_pointclouds (d2r:405-410,  */

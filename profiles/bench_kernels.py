@@ -61,7 +61,12 @@ def emit(name, unit_name, units, ms, alg_bytes, cpu=None, **extra):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of kernels to run, e.g. K1,K2 (default all)")
     args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+
+    def want(k):
+        return not only or k in only
     import torch
     from oracle import capi
     from textureless_3d_reconstruction_b200.runtime import TSDFVolume, get_context
@@ -80,7 +85,7 @@ def main():
     h_depth0, h_bgr0 = depth[0].cpu().numpy(), bgr[0].cpu().numpy()
 
     # ------------------------------------------------------------------ K1
-    for s in (1, 2, 4):
+    for s in ((1, 2, 4) if want("K1") else ()):
         Hs, Ws = -(-H // s), -(-W // s)
         P = Hs * Ws
         o_xyz = torch.empty((P, 3), dtype=torch.float32, device=dev)
@@ -110,6 +115,26 @@ def main():
                   "frames_per_s_numpy_restatement_1core": (1 / cpu_np) if cpu_np > 1e-4 else None},
              valid_points=nvalid, sampled_pixels=P)
 
+    if want("K1"):
+        # batched entry point: all NF frames, one launch per 32 frames, vstack-ordered output
+        for s in (1, 2, 4):
+            Hs, Ws = -(-H // s), -(-W // s)
+            P = Hs * Ws
+            frames = ctx.make_backproject_frames([depth[i] for i in range(NF)], [bgr[i] for i in range(NF)],
+                                                 [(poses[i][:, :3], poses[i][:, 3:4]) for i in range(NF)])
+            o_xyz = torch.empty((P * NF, 3), dtype=torch.float32, device=dev)
+            o_rgb = torch.empty((P * NF, 3), dtype=torch.uint8, device=dev)
+            offs = torch.zeros(NF + 1, dtype=torch.int64, device=dev)
+
+            def k1b(i, s=s):
+                ctx.backproject_batch(frames, NF, H, W, fx=K4[0], fy=K4[1], cx=K4[2], cy=K4[3], subsample=s,
+                                      min_depth=0.1, max_depth=50.0, out_xyz=o_xyz, out_rgb=o_rgb, out_offsets=offs)
+            ms = gpu_time(k1b, 20)
+            nvalid = int(offs[-1].item())
+            emit(f"K1 backproject_batch s={s} ({NF} frames/call)", "frames", NF, ms, 7 * P * NF + 15 * nvalid,
+                 valid_points=nvalid, sampled_pixels=P * NF)
+            del o_xyz, o_rgb
+
     # ------------------------------------------------------------------ fused cloud for K2/K3/K7
     NC = 4 if args.quick else 16
     clouds, cols = [], []
@@ -123,14 +148,19 @@ def main():
     rgb = torch.cat(cols).contiguous()
     del clouds, cols
     N = pts.shape[0]
-    for voxel in (0.005, 0.01, 0.02):
+    for voxel in ((0.005, 0.01, 0.02) if want("K2") else ()):
         res = {}
 
         def k2(i, voxel=voxel):
             res["r"] = ctx.voxel_downsample(pts, rgb, voxel, sorted_output=False, want_idx=False)
-        t0 = time.perf_counter()
-        k2(0)
-        torch.cuda.synchronize()
+        walls = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            k2(0)
+            torch.cuda.synchronize()
+            walls.append(round((time.perf_counter() - t0) * 1e3, 3))
+        print(f"K2 v={voxel} host wall per call (ms): {walls}", file=sys.stderr, flush=True)
         ms = gpu_time(k2, 5, warm=1)
         M = res["r"]["m"]
         ns = min(N, 4_000_000)
@@ -148,32 +178,36 @@ def main():
     P64 = ds["points"].contiguous()
     M = P64.shape[0]
 
-    def k3(i):
-        ctx.statistical_outlier(P64, 20, 2.0)
-    ms = gpu_time(k3, 3, warm=1)
-    ns = min(M, 300_000)
-    hp = P64[:ns].cpu().numpy()
-    t0 = time.perf_counter()
-    capi.statistical_outlier(hp, 20, 2.0)
-    cpu_s = time.perf_counter() - t0
-    emit("K3 statistical_outlier nb=20", "points", M, ms, 24 * M + M,
-         cpu={"points_per_s": ns / cpu_s, "cores": cores, "sample": f"first {ns} of the downsampled points"},
-         uncached_upper_bound_bytes=24 * M * 21)
+    if want("K3"):
+        def k3(i):
+            ctx.statistical_outlier(P64, 20, 2.0)
+        ms = gpu_time(k3, 3, warm=1)
+        ns = min(M, 300_000)
+        hp = P64[:ns].cpu().numpy()
+        t0 = time.perf_counter()
+        capi.statistical_outlier(hp, 20, 2.0)
+        cpu_s = time.perf_counter() - t0
+        emit("K3 statistical_outlier nb=20", "points", M, ms, 24 * M + M,
+             cpu={"points_per_s": ns / cpu_s, "cores": cores, "sample": f"first {ns} of the downsampled points"},
+             uncached_upper_bound_bytes=24 * M * 21)
 
     # K7 normals on the same cloud (f32)
-    P32 = P64.to(torch.float32).contiguous()
+    if want("K7"):
+        P32 = P64.to(torch.float32).contiguous()
 
-    def k7(i):
-        ctx.estimate_normals(P32, 30)
-    ms = gpu_time(k7, 3, warm=1)
-    ns = min(M, 300_000)
-    hp = P32[:ns].cpu().numpy()
-    t0 = time.perf_counter()
-    capi.estimate_normals(hp, 30)
-    cpu_s = time.perf_counter() - t0
-    emit("K7 estimate_normals knn=30", "points", M, ms, 24 * M,
-         cpu={"points_per_s": ns / cpu_s, "cores": cores, "sample": f"first {ns} points"})
+        def k7(i):
+            ctx.estimate_normals(P32, 30)
+        ms = gpu_time(k7, 3, warm=1)
+        ns = min(M, 300_000)
+        hp = P32[:ns].cpu().numpy()
+        t0 = time.perf_counter()
+        capi.estimate_normals(hp, 30)
+        cpu_s = time.perf_counter() - t0
+        emit("K7 estimate_normals knn=30", "points", M, ms, 24 * M,
+             cpu={"points_per_s": ns / cpu_s, "cores": cores, "sample": f"first {ns} points"})
     del pts, rgb
+    if only and not (only & {"K4", "K6", "K8", "K9"}):
+        return
 
     # ------------------------------------------------------------------ K4 / K6 on a fused volume
     vol = TSDFVolume(0.01, 0.04, block_capacity=120_000, ctx=ctx)

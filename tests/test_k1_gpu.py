@@ -113,6 +113,41 @@ def test_edge_shapes_and_conf_mask(ctx, oracle):
     assert np.array_equal(xyz[: len(o_xyz)].cpu().numpy(), o_xyz)
 
 
+@pytest.mark.parametrize("n_frames,H,W,s", [(1, 33, 47, 1), (5, 120, 68, 2), (40, 64, 48, 1), (70, 31, 29, 3)])
+def test_batch_equals_per_frame_vstack(ctx, oracle, n_frames, H, W, s):
+    """t3d_backproject_batch == the reference's per-frame loop + np.vstack (d2r:566-581, 401-402):
+    bit-identical rows, frame-ordered, offsets = per-frame counts; > 32 frames spans several launches."""
+    import torch
+    from textureless_3d_reconstruction_b200 import synthetic as S
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    depths, bgrs, poses = [], [], []
+    rng = np.random.default_rng(n_frames)
+    for i in range(n_frames):
+        d, c, T = S.synth_frame(1, i, H, W, *K)
+        d = d.copy()
+        d[rng.uniform(size=d.shape) < 0.2] = 0.0            # ragged validity per frame
+        if i == 1:
+            d[:] = 0.0                                        # an empty frame in the middle
+        depths.append(torch.from_numpy(d).cuda())
+        bgrs.append(torch.from_numpy(c).cuda())
+        poses.append((T[:, :3].copy(), T[:, 3:4].copy()))
+    frames = ctx.make_backproject_frames(depths, bgrs, poses)
+    xyz, rgb, offs = ctx.backproject_batch(frames, n_frames, H, W, fx=K[0], fy=K[1], cx=K[2], cy=K[3], subsample=s,
+                                           max_depth=50.0)
+    offs = offs.cpu().numpy()
+    assert offs[0] == 0 and np.all(np.diff(offs) >= 0)
+    for i in range(n_frames):
+        o_xyz, o_rgb = oracle.backproject(depths[i].cpu().numpy(), bgrs[i].cpu().numpy(), *K, pose=poses[i],
+                                          max_depth=50.0, subsample=s)
+        a, b = int(offs[i]), int(offs[i + 1])
+        assert b - a == len(o_xyz), i
+        assert np.array_equal(xyz[a:b].cpu().numpy().view(np.uint32), o_xyz.view(np.uint32)), i
+        assert np.array_equal(rgb[a:b].cpu().numpy(), o_rgb), i
+    if n_frames > 1:
+        assert offs[2] == offs[1]                             # the empty frame owns no rows
+
+
 def test_capacity_and_argument_errors(ctx):
     import torch
     from textureless_3d_reconstruction_b200._lib import T3DError

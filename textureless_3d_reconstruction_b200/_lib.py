@@ -33,6 +33,11 @@ class BackprojectParams(C.Structure):
     ]
 
 
+class BackprojectFrame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("bgr", C.c_void_p), ("conf_mask", C.c_void_p),
+                ("R", C.c_double * 9), ("t", C.c_double * 3)]
+
+
 class TsdfParams(C.Structure):
     _fields_ = [
         ("voxel_size", C.c_float), ("sdf_trunc", C.c_float), ("block_res", C.c_int32),
@@ -64,6 +69,8 @@ _SIGS = {
     "t3d_destroy": (None, [_VP]),
     "t3d_launch_count": (_I64, [_VP]),
     "t3d_backproject": (_I, [_VP, _VP, _VP, _VP, C.POINTER(BackprojectParams), _VP, _VP, _I64, _VP, _VP]),
+    "t3d_backproject_batch": (_I, [_VP, C.POINTER(BackprojectFrame), _I, C.POINTER(BackprojectParams), _VP, _VP, _I64,
+                                   _VP, _VP]),
     "t3d_voxel_downsample": (_I, [_VP, _VP, _I, _VP, _I64, _D, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "t3d_bounds": (_I, [_VP, _VP, _I, _I64, _VP, _VP, _VP]),
     "t3d_statistical_outlier": (_I, [_VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),

@@ -95,10 +95,26 @@ struct t3d_ctx {
   std::vector<ProjTable> proj;
   DevBuf scan_state;  // decoupled look-back tile descriptors + ticket
   // generic scratch (hash tables, grid cells, reductions)
-  DevBuf scratch[8];
+  DevBuf scratch[12];
   // pinned host staging for small synchronous results
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+};
+
+// host-side phase timing, printed to stderr when T3D_TRACE is set (debug aid)
+#include <chrono>
+struct T3DTrace {
+  bool on;
+  const char* fn;
+  std::chrono::steady_clock::time_point t;
+  explicit T3DTrace(const char* f) : on(getenv("T3D_TRACE") != nullptr), fn(f), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* label) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[t3d trace] %s: %-18s %9.3f ms\n", fn, label,
+            std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
 };
 
 inline cudaStream_t as_stream(t3d_stream s) {

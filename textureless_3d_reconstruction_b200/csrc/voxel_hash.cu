@@ -64,96 +64,185 @@ __global__ void bounds_final_kernel(const double* partial, int nblocks, double* 
 }
 
 // ---------------------------------------------------------------------------
-// voxel hash
+// voxel hash — two passes over the points, both warp-aggregated.
+//
+//   pass 1 (voxel_keys_kernel)   key table only: the lanes of a warp that fall
+//       into the same voxel elect one leader (__match_any_sync); only leaders
+//       touch the table.  The CAS winner of a slot takes the next dense voxel id
+//       from a counter and records key_of_id[id].  Depth-map clouds put tens of
+//       neighbouring points into one voxel, so this removes >90 % of the table
+//       traffic and all same-address CAS storms.
+//   (host reads M — the only size the accumulators need)
+//   pass 2 (voxel_accum_kernel)  leaders look their voxel id up, the warp
+//       reduces each group (f64 xor-shuffle tree for xyz, redux.sync for the
+//       integer colour sums and the count) and the leader issues ONE red.add
+//       per accumulator.  Accumulators are M 64-byte records (one per voxel),
+//       not per-slot, so nothing of size O(table) is ever zeroed or scanned.
+//
+// Memory: 12 B per table slot (>= 2 N slots) + 8 B per point of key scratch + 64 B
+// per output voxel, instead of 48 B per slot.  f64 sums of f32 inputs that lie
+// within one voxel are exact, so the means do not depend on the reduction order.
 // ---------------------------------------------------------------------------
+// one 64-byte, 64-byte-aligned accumulator per output voxel: a group's seven
+// reductions land in two adjacent 32 B sectors instead of seven scattered ones
+struct __align__(64) VoxAcc {
+  double sx, sy, sz;
+  unsigned r, g, b, cnt;
+  unsigned pad[6];
+};
+
 struct VoxTable {
-  unsigned long long* keys;
-  double* sx; double* sy; double* sz;
-  unsigned* sr; unsigned* sg; unsigned* sb;
-  unsigned* cnt;
-  unsigned long long mask;
-  int* flags;  // [0] table full, [1] index out of packable range
+  unsigned long long* keys;   // cap slots, T3D_KEY_EMPTY = free
+  unsigned* ids;              // cap slots: dense voxel id of the slot's key
+  unsigned long long mask;    // cap - 1
+  unsigned long long* key_of_id;  // n entries (M used)
+  unsigned long long* counter;    // [0] M
+  int* flags;                 // [0] table full, [1] index out of packable range
+  struct VoxAcc* acc;         // M records
+  int sh_x, sh_y;             // key = ix << sh_x | iy << sh_y | iz (ascending key == (x,y,z) order)
+};
+
+struct VoxGrid {
+  double minx, miny, minz, voxel;
+  double lim_x, lim_y, lim_z;  // number of cells per axis (exclusive upper bound of the index)
 };
 
 template <typename T>
+__device__ __forceinline__ bool voxel_key_of(const T* __restrict__ xyz, long long i,
+                                             const VoxGrid& g, const VoxTable& tb, double& px,
+                                             double& py, double& pz, unsigned long long& key) {
+  px = (double)xyz[i * 3 + 0];
+  py = (double)xyz[i * 3 + 1];
+  pz = (double)xyz[i * 3 + 2];
+  // floor((p - minb) / v): IEEE subtract + true division, no contraction
+  const double fx = floor(__ddiv_rn(__dsub_rn(px, g.minx), g.voxel));
+  const double fy = floor(__ddiv_rn(__dsub_rn(py, g.miny), g.voxel));
+  const double fz = floor(__ddiv_rn(__dsub_rn(pz, g.minz), g.voxel));
+  if (!(fx >= 0.0 && fx < g.lim_x && fy >= 0.0 && fy < g.lim_y && fz >= 0.0 && fz < g.lim_z)) {
+    tb.flags[1] = 1;
+    return false;
+  }
+  key = ((unsigned long long)(unsigned)(int)fx << tb.sh_x) |
+        ((unsigned long long)(unsigned)(int)fy << tb.sh_y) | (unsigned long long)(unsigned)(int)fz;
+  return true;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-    voxel_insert_kernel(const T* __restrict__ xyz, const uint8_t* __restrict__ rgb,
-                        long long n, double minx, double miny, double minz, double voxel,
-                        const __grid_constant__ VoxTable tb) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const double px = (double)xyz[i * 3 + 0], py = (double)xyz[i * 3 + 1],
-                 pz = (double)xyz[i * 3 + 2];
-    // floor((p - minb) / v): IEEE subtract + true division, no contraction
-    const double fx = floor(__ddiv_rn(__dsub_rn(px, minx), voxel));
-    const double fy = floor(__ddiv_rn(__dsub_rn(py, miny), voxel));
-    const double fz = floor(__ddiv_rn(__dsub_rn(pz, minz), voxel));
-    if (!(fx >= 0.0 && fx < 2097152.0 && fy >= 0.0 && fy < 2097152.0 && fz >= 0.0 &&
-          fz < 2097152.0)) {
-      tb.flags[1] = 1;
-      continue;
-    }
-    const unsigned long long key = ((unsigned long long)(unsigned)(int)fx << 42) |
-                                   ((unsigned long long)(unsigned)(int)fy << 21) |
-                                   (unsigned long long)(unsigned)(int)fz;
+    voxel_keys_kernel(const T* __restrict__ xyz, long long n, const __grid_constant__ VoxGrid g,
+                      const __grid_constant__ VoxTable tb) {
+  const unsigned lane = lane_id();
+  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < n;
+       base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + lane;
+    double px, py, pz;
+    unsigned long long key = 0;
+    const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const unsigned peers = __match_any_sync(act, key);
+    if ((int)lane != __ffs(peers) - 1) continue;
     unsigned long long slot = mix64(key) & tb.mask;
     bool placed = false;
     for (unsigned long long probe = 0; probe <= tb.mask; ++probe) {
       unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + slot));
-      if (k == T3D_KEY_EMPTY) k = atomicCAS(tb.keys + slot, T3D_KEY_EMPTY, key);
-      if (k == T3D_KEY_EMPTY || k == key) { placed = true; break; }
+      if (k == T3D_KEY_EMPTY) {
+        k = atomicCAS(tb.keys + slot, T3D_KEY_EMPTY, key);
+        if (k == T3D_KEY_EMPTY) {  // this thread created the voxel
+          const unsigned long long id = atomicAdd(tb.counter, 1ull);
+          tb.ids[slot] = (unsigned)id;
+          tb.key_of_id[id] = key;
+          placed = true;
+          break;
+        }
+      }
+      if (k == key) { placed = true; break; }
       slot = (slot + 1) & tb.mask;
     }
-    if (!placed) { tb.flags[0] = 1; continue; }
-    atomicAdd(tb.sx + slot, px);
-    atomicAdd(tb.sy + slot, py);
-    atomicAdd(tb.sz + slot, pz);
-    if (rgb) {
-      atomicAdd(tb.sr + slot, (unsigned)rgb[i * 3 + 0]);
-      atomicAdd(tb.sg + slot, (unsigned)rgb[i * 3 + 1]);
-      atomicAdd(tb.sb + slot, (unsigned)rgb[i * 3 + 2]);
-    }
-    atomicAdd(tb.cnt + slot, 1u);
+    if (!placed) tb.flags[0] = 1;
   }
 }
 
-// occupied slots -> dense list of (key, slot); warp-aggregated append
-__global__ void voxel_collect_kernel(const __grid_constant__ VoxTable tb,
-                                     unsigned long long* out_keys, unsigned* out_slots,
-                                     unsigned long long* out_m) {
-  const unsigned long long cap = tb.mask + 1;
-  for (unsigned long long s0 = (unsigned long long)blockIdx.x * blockDim.x; s0 < cap;
-       s0 += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long s = s0 + threadIdx.x;
-    const bool occ = s < cap && tb.keys[s] != T3D_KEY_EMPTY;
-    const unsigned b = __ballot_sync(0xffffffffu, occ);
-    if (b == 0) continue;
-    unsigned long long base = 0;
-    if (lane_id() == 0) base = atomicAdd(out_m, (unsigned long long)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (occ) {
-      const unsigned long long o = base + __popc(b & lanemask_lt());
-      out_keys[o] = tb.keys[s];
-      out_slots[o] = (unsigned)s;
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    voxel_accum_kernel(const T* __restrict__ xyz, const uint8_t* __restrict__ rgb, long long n,
+                       const __grid_constant__ VoxGrid g, const __grid_constant__ VoxTable tb) {
+  const unsigned lane = lane_id();
+  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < n;
+       base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + lane;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    unsigned long long key = 0;
+    const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
+    unsigned cr = 0, cg = 0, cb = 0;
+    if (valid && rgb) { cr = rgb[i * 3 + 0]; cg = rgb[i * 3 + 1]; cb = rgb[i * 3 + 2]; }
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    unsigned peers = 0;
+    unsigned id = 0;
+    if (valid) {
+      peers = __match_any_sync(act, key);
+      if ((int)lane == __ffs(peers) - 1) {  // leader: find the voxel id (pass 1 inserted every key)
+        unsigned long long slot = mix64(key) & tb.mask;
+        while (tb.keys[slot] != key) slot = (slot + 1) & tb.mask;
+        id = tb.ids[slot];
+      }
+    }
+    unsigned remaining = act;
+    while (remaining) {  // warp-uniform loop over the distinct voxels of this warp
+      const int L = __ffs(remaining) - 1;
+      const unsigned grp = __shfl_sync(0xffffffffu, peers, L);
+      remaining &= ~grp;
+      if (grp == (1u << L)) {  // singleton group: no reduction needed
+        if ((int)lane == L) {
+          VoxAcc* a = tb.acc + id;
+          atomicAdd(&a->sx, px); atomicAdd(&a->sy, py); atomicAdd(&a->sz, pz);
+          if (rgb) { atomicAdd(&a->r, cr); atomicAdd(&a->g, cg); atomicAdd(&a->b, cb); }
+          atomicAdd(&a->cnt, 1u);
+        }
+        continue;
+      }
+      const bool mem = (grp >> lane) & 1u;
+      const double ax = warp_sum_f64(mem ? px : 0.0);
+      const double ay = warp_sum_f64(mem ? py : 0.0);
+      const double az = warp_sum_f64(mem ? pz : 0.0);
+      unsigned ar = 0, ag = 0, ab = 0;
+      if (rgb) {
+        ar = __reduce_add_sync(0xffffffffu, mem ? cr : 0u);
+        ag = __reduce_add_sync(0xffffffffu, mem ? cg : 0u);
+        ab = __reduce_add_sync(0xffffffffu, mem ? cb : 0u);
+      }
+      if ((int)lane == L) {
+        VoxAcc* a = tb.acc + id;
+        atomicAdd(&a->sx, ax); atomicAdd(&a->sy, ay); atomicAdd(&a->sz, az);
+        if (rgb) { atomicAdd(&a->r, ar); atomicAdd(&a->g, ag); atomicAdd(&a->b, ab); }
+        atomicAdd(&a->cnt, (unsigned)__popc(grp));
+      }
     }
   }
 }
 
+// order[i] = voxel id written at output row i (identity when unsorted)
 __global__ void voxel_finalize_kernel(const __grid_constant__ VoxTable tb,
-                                      const unsigned* __restrict__ slots, long long m,
+                                      const unsigned* __restrict__ order, long long m,
                                       int has_rgb, double* out_xyz, uint8_t* out_rgb,
                                       unsigned* out_rgb_sum, unsigned* out_count,
                                       int* out_idx) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m;
        i += (long long)gridDim.x * blockDim.x) {
-    const unsigned s = slots[i];
-    const unsigned c = tb.cnt[s];
+    const unsigned s = order ? order[i] : (unsigned)i;
+    const VoxAcc a = tb.acc[s];
+    const unsigned c = a.cnt;
     const double dn = (double)c;
-    out_xyz[i * 3 + 0] = __ddiv_rn(tb.sx[s], dn);
-    out_xyz[i * 3 + 1] = __ddiv_rn(tb.sy[s], dn);
-    out_xyz[i * 3 + 2] = __ddiv_rn(tb.sz[s], dn);
-    const unsigned r = has_rgb ? tb.sr[s] : 0u, g = has_rgb ? tb.sg[s] : 0u,
-                   b = has_rgb ? tb.sb[s] : 0u;
+    out_xyz[i * 3 + 0] = __ddiv_rn(a.sx, dn);
+    out_xyz[i * 3 + 1] = __ddiv_rn(a.sy, dn);
+    out_xyz[i * 3 + 2] = __ddiv_rn(a.sz, dn);
+    const unsigned r = has_rgb ? a.r : 0u, g = has_rgb ? a.g : 0u, b = has_rgb ? a.b : 0u;
     if (out_rgb && has_rgb) {
       // (mean(c/255) * 255).astype(uint8) — truncation, d2r:417-418
       out_rgb[i * 3 + 0] = (uint8_t)(int)__dmul_rn(__ddiv_rn(__ddiv_rn((double)r, 255.0), dn), 255.0);
@@ -163,12 +252,18 @@ __global__ void voxel_finalize_kernel(const __grid_constant__ VoxTable tb,
     if (out_rgb_sum) { out_rgb_sum[i * 3] = r; out_rgb_sum[i * 3 + 1] = g; out_rgb_sum[i * 3 + 2] = b; }
     if (out_count) out_count[i] = c;
     if (out_idx) {
-      const unsigned long long k = tb.keys[s];
-      out_idx[i * 3 + 0] = (int)((k >> 42) & 0x1FFFFF);
-      out_idx[i * 3 + 1] = (int)((k >> 21) & 0x1FFFFF);
-      out_idx[i * 3 + 2] = (int)(k & 0x1FFFFF);
+      const unsigned long long k = tb.key_of_id[s];
+      out_idx[i * 3 + 0] = (int)(k >> tb.sh_x);
+      out_idx[i * 3 + 1] = (int)((k >> tb.sh_y) & ((1ull << (tb.sh_x - tb.sh_y)) - 1ull));
+      out_idx[i * 3 + 2] = (int)(k & ((1ull << tb.sh_y) - 1ull));
     }
   }
+}
+
+__global__ void iota_kernel(unsigned* v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    v[i] = (unsigned)i;
 }
 
 // ---------------------------------------------------------------------------
@@ -419,10 +514,15 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
     return T3D_OK;
   }
   T3D_REQUIRE(xyz && out_xyz && n > 0, "t3d_voxel_downsample: null xyz/out_xyz");
+  T3D_REQUIRE(n < (1ll << 32) - 64, "t3d_voxel_downsample: more than 2^32 points in one call");
+  T3DTrace tr("voxel_downsample");
   double mn[3], mx[3];
   int rc = t3d_bounds(ctx, xyz, xyz_is_f64, n, mn, mx, stream);
   if (rc != T3D_OK) return rc;
+  tr.mark("bounds+sync");
   double minb[3];
+  int bits[3];
+  VoxGrid g;
   for (int c = 0; c < 3; ++c) {
     minb[c] = min_bound_h ? min_bound_h[c] : mn[c] - voxel * 0.5;
     if (out_min_bound_h) out_min_bound_h[c] = minb[c];
@@ -435,59 +535,54 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
       t3d_set_error("t3d_voxel_downsample: grid exceeds 2^21 voxels per axis (or min_bound > data)");
       return T3D_E_NUMERIC;
     }
+    // cells per axis (+2 guards the rounding of the device-side division)
+    const double cells = floor(ext / voxel) + 2.0;
+    bits[c] = 1;
+    while ((double)(1ull << bits[c]) < cells) ++bits[c];
   }
-  // table capacity: load factor <= 0.5 w.r.t. the worst case (every point its own voxel)
+  g.minx = minb[0]; g.miny = minb[1]; g.minz = minb[2]; g.voxel = voxel;
+  g.lim_x = (double)(1ull << bits[0]); g.lim_y = (double)(1ull << bits[1]); g.lim_z = (double)(1ull << bits[2]);
+  const int key_bits = bits[0] + bits[1] + bits[2];
+
+  // key table: load factor <= 0.5 w.r.t. the worst case (every point its own voxel)
   unsigned long long cap = 1024;
   while (cap < 2ull * (unsigned long long)n) cap <<= 1;
-  const size_t per_slot = 8 + 3 * 8 + 3 * 4 + 4;
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  while (cap > 1024 && cap * per_slot > free_b / 2 + ctx->scratch[0].cap && cap > (unsigned long long)n)
-    cap >>= 1;  // degrade to load factor <= 1 before failing
-  rc = ctx->scratch[0].reserve(cap * per_slot);
-  if (rc != T3D_OK) return rc;
-  uint8_t* base = ctx->scratch[0].as<uint8_t>();
+  if (cap * 12 > ctx->scratch[0].cap && cap * 12 > (8ull << 30)) {  // only probe the driver for big tables
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    while (cap > 1024 && cap * 12 > free_b / 2 + ctx->scratch[0].cap && cap / 2 > (unsigned long long)n + n / 4)
+      cap >>= 1;  // degrade to load factor <= 0.8 before failing
+  }
+  if ((rc = ctx->scratch[0].reserve(cap * 12)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[1].reserve(64)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[2].reserve((size_t)n * 8)) != T3D_OK) return rc;
   VoxTable tb;
-  tb.keys = reinterpret_cast<unsigned long long*>(base);
-  tb.sx = reinterpret_cast<double*>(base + cap * 8);
-  tb.sy = tb.sx + cap;
-  tb.sz = tb.sy + cap;
-  tb.sr = reinterpret_cast<unsigned*>(base + cap * 32);
-  tb.sg = tb.sr + cap;
-  tb.sb = tb.sg + cap;
-  tb.cnt = tb.sb + cap;
+  memset(&tb, 0, sizeof(tb));
+  tb.keys = ctx->scratch[0].as<unsigned long long>();
+  tb.ids = reinterpret_cast<unsigned*>(tb.keys + cap);
   tb.mask = cap - 1;
-  rc = ctx->scratch[1].reserve(64);
-  if (rc != T3D_OK) return rc;
+  tb.key_of_id = ctx->scratch[2].as<unsigned long long>();
   tb.flags = ctx->scratch[1].as<int>();
-  unsigned long long* d_m = reinterpret_cast<unsigned long long*>(tb.flags + 4);
+  tb.counter = reinterpret_cast<unsigned long long*>(tb.flags + 4);
+  tb.sh_y = bits[2];
+  tb.sh_x = bits[1] + bits[2];
+  tr.mark("reserve");
   T3D_CUDA(cudaMemsetAsync(tb.keys, 0xFF, cap * 8, st));
-  T3D_CUDA(cudaMemsetAsync(base + cap * 8, 0, cap * (per_slot - 8), st));
   T3D_CUDA(cudaMemsetAsync(tb.flags, 0, 64, st));
 
-  const int grid = ctx->num_sms * 8;
+  const long long warps = (n + 31) / 32;
+  const long long want = (warps + 7) / 8;  // 256-thread CTAs
+  const int grid = (int)(want < (long long)ctx->num_sms * 16 ? want : (long long)ctx->num_sms * 16);
   if (xyz_is_f64)
-    voxel_insert_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), rgb, n,
-                                                      minb[0], minb[1], minb[2], voxel, tb);
+    voxel_keys_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), n, g, tb);
   else
-    voxel_insert_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), rgb, n,
-                                                     minb[0], minb[1], minb[2], voxel, tb);
-  T3D_LAUNCH_CHECK();
-  ctx->launches++;
-
-  // collect occupied slots
-  rc = ctx->scratch[2].reserve((size_t)n * 8);   // keys   (M <= n)
-  if (rc != T3D_OK) return rc;
-  rc = ctx->scratch[3].reserve((size_t)n * 4);   // slots
-  if (rc != T3D_OK) return rc;
-  unsigned long long* ckeys = ctx->scratch[2].as<unsigned long long>();
-  unsigned* cslots = ctx->scratch[3].as<unsigned>();
-  voxel_collect_kernel<<<grid, 256, 0, st>>>(tb, ckeys, cslots, d_m);
+    voxel_keys_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), n, g, tb);
   T3D_LAUNCH_CHECK();
   ctx->launches++;
   int* h = reinterpret_cast<int*>(ctx->pinned);
   T3D_CUDA(cudaMemcpyAsync(h, tb.flags, 64, cudaMemcpyDeviceToHost, st));
   T3D_CUDA(cudaStreamSynchronize(st));
+  tr.mark("pass1+sync");
   if (h[0]) { t3d_set_error("t3d_voxel_downsample: hash table full"); return T3D_E_CAPACITY; }
   if (h[1]) { t3d_set_error("t3d_voxel_downsample: voxel index out of range"); return T3D_E_NUMERIC; }
   const long long m = (long long)*reinterpret_cast<unsigned long long*>(h + 4);
@@ -495,24 +590,45 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
     t3d_set_error("t3d_voxel_downsample: capacity %lld < voxels %lld", (long long)capacity, m);
     return T3D_E_CAPACITY;
   }
+
+  // accumulators: m 64-byte records (cudaMalloc returns >= 256 B aligned memory)
+  if ((rc = ctx->scratch[8].reserve((size_t)m * sizeof(VoxAcc) + 64)) != T3D_OK) return rc;
+  tb.acc = ctx->scratch[8].as<VoxAcc>();
+  T3D_CUDA(cudaMemsetAsync(tb.acc, 0, (size_t)m * sizeof(VoxAcc), st));
+  if (xyz_is_f64)
+    voxel_accum_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), rgb, n, g, tb);
+  else
+    voxel_accum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), rgb, n, g, tb);
+  T3D_LAUNCH_CHECK();
+  ctx->launches++;
+
+  const unsigned* order = nullptr;
+  const int fgrid = ctx->num_sms * 8;
   if (sorted && m > 1) {
-    rc = ctx->scratch[4].reserve((size_t)m * 8);
+    if ((rc = ctx->scratch[3].reserve((size_t)m * 4)) != T3D_OK) return rc;
+    if ((rc = ctx->scratch[4].reserve((size_t)m * 8)) != T3D_OK) return rc;
+    if ((rc = ctx->scratch[5].reserve((size_t)m * 4)) != T3D_OK) return rc;
+    if ((rc = ctx->scratch[9].reserve((size_t)m * 8)) != T3D_OK) return rc;
+    unsigned* ids = ctx->scratch[3].as<unsigned>();
+    iota_kernel<<<fgrid, 256, 0, st>>>(ids, m);
+    T3D_LAUNCH_CHECK();
+    ctx->launches++;
+    // sort a copy of the keys (key_of_id must stay addressable by id for out_idx)
+    unsigned long long* skeys = ctx->scratch[9].as<unsigned long long>();
+    T3D_CUDA(cudaMemcpyAsync(skeys, tb.key_of_id, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    rc = t3d_radix_sort_u64(ctx, skeys, ids, ctx->scratch[4].as<unsigned long long>(),
+                            ctx->scratch[5].as<unsigned>(), m, key_bits, st);
     if (rc != T3D_OK) return rc;
-    rc = ctx->scratch[5].reserve((size_t)m * 4);
-    if (rc != T3D_OK) return rc;
-    rc = t3d_radix_sort_u64(ctx, ckeys, cslots, ctx->scratch[4].as<unsigned long long>(),
-                            ctx->scratch[5].as<unsigned>(), m, 63, st);
-    if (rc != T3D_OK) return rc;
+    order = ids;
   }
   if (m > 0) {
-    voxel_finalize_kernel<<<grid, 256, 0, st>>>(tb, cslots, m, rgb != nullptr, out_xyz, out_rgb,
-                                                out_rgb_sum, out_count, out_vox_idx);
+    voxel_finalize_kernel<<<fgrid, 256, 0, st>>>(tb, order, m, rgb != nullptr, out_xyz, out_rgb,
+                                                 out_rgb_sum, out_count, out_vox_idx);
     T3D_LAUNCH_CHECK();
     ctx->launches++;
   }
-  const int64_t m64 = m;
-  T3D_CUDA(cudaMemcpyAsync(out_m, &m64, sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  T3D_CUDA(cudaStreamSynchronize(st));
+  T3D_CUDA(cudaMemcpyAsync(out_m, tb.counter, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (tr.on) { cudaStreamSynchronize(st); tr.mark("pass2+finalize"); }
   return T3D_OK;
 }
 

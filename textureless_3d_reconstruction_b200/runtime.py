@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import BackprojectParams, FrameView, IcpResult, TsdfParams, check
+from ._lib import BackprojectFrame, BackprojectParams, FrameView, IcpResult, TsdfParams, check
 
 _contexts: dict[int, "Context"] = {}
 
@@ -122,6 +122,45 @@ class Context:
         check(self.lib.t3d_backproject(self.handle, _ptr(depth), _ptr(bgr), _ptr(conf_mask), C.byref(p),
                                        _ptr(out_xyz), _ptr(out_rgb), out_xyz.shape[0], _ptr(out_n), _stream()))
         return out_xyz, out_rgb, out_n
+
+    def make_backproject_frames(self, depths, bgrs, poses=None, conf_masks=None):
+        """Host-side descriptor array for backproject_batch (build once, reuse)."""
+        n = len(depths)
+        arr = (BackprojectFrame * n)()
+        for i in range(n):
+            arr[i].depth = depths[i].data_ptr()
+            arr[i].bgr = bgrs[i].data_ptr() if bgrs is not None and bgrs[i] is not None else None
+            arr[i].conf_mask = conf_masks[i].data_ptr() if conf_masks is not None and conf_masks[i] is not None else None
+            if poses is not None:
+                arr[i].R[:] = np.ascontiguousarray(poses[i][0], np.float64).reshape(9).tolist()
+                arr[i].t[:] = np.ascontiguousarray(poses[i][1], np.float64).reshape(3).tolist()
+        return arr
+
+    def backproject_batch(self, frames, n_frames, H, W, *, fx, fy, cx, cy, subsample=1, scale=1.0,
+                          scale_is_f64=False, depth_is_f64=False, min_depth=0.1, max_depth=50.0, has_pose=True,
+                          has_color=True, rgb_out_f32=False, out_xyz=None, out_rgb=None, out_offsets=None):
+        """K1 over `n_frames` frames (descriptors from make_backproject_frames) with one launch
+        per 32 frames; the output is the frame-ordered concatenation (the reference's per-frame
+        loop + np.vstack).  Returns (xyz[cap,3], rgb[cap,3]|None, offsets int64[n+1]) on device."""
+        torch = _torch()
+        p = BackprojectParams()
+        p.H, p.W, p.subsample = int(H), int(W), int(subsample)
+        p.depth_is_f64, p.scale_is_f64 = int(bool(depth_is_f64)), int(bool(scale_is_f64))
+        p.has_pose, p.rgb_out_f32, p.has_color = int(bool(has_pose)), int(bool(rgb_out_f32)), int(bool(has_color))
+        p.fx, p.fy, p.cx, p.cy = float(fx), float(fy), float(cx), float(cy)
+        p.scale, p.min_depth, p.max_depth = float(scale), float(min_depth), float(max_depth)
+        s = int(subsample)
+        cap = (-(-H // s)) * (-(-W // s)) * n_frames if s >= 1 else 0
+        if out_xyz is None:
+            out_xyz = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=self.device)
+        if has_color and out_rgb is None:
+            out_rgb = torch.empty((max(cap, 1), 3), dtype=torch.float32 if rgb_out_f32 else torch.uint8,
+                                  device=self.device)
+        if out_offsets is None:
+            out_offsets = torch.zeros(n_frames + 1, dtype=torch.int64, device=self.device)
+        check(self.lib.t3d_backproject_batch(self.handle, frames, int(n_frames), C.byref(p), _ptr(out_xyz),
+                                             _ptr(out_rgb), out_xyz.shape[0], _ptr(out_offsets), _stream()))
+        return out_xyz, out_rgb, out_offsets
 
     # ------------------------------------------------------------------ K2
     def voxel_downsample(self, xyz, rgb, voxel_size, *, min_bound=None, sorted_output=True,
