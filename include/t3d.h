@@ -245,6 +245,18 @@ int t3d_tsdf_extract_points(t3d_tsdf* v, float weight_threshold, float* xyz,
                             float* nrm, uint8_t* rgb, int64_t capacity,
                             int64_t* out_n, t3d_stream stream);
 
+/* K6 restricted to the blocks a camera can see (frame-to-model tracking, cfg 3:
+ * the ICP target is the model surface inside the predicted view).  A block is
+ * kept iff its bounding sphere (centre (key+0.5)*8*voxel, radius sqrt(3)/2*8*voxel)
+ * reaches into depth (0, depth_max) and into the image rectangle of view_h
+ * (K, T_cw; depth/bgr pointers ignored).  out_blocks_h (nullable, host): number
+ * of blocks selected.  Synchronous (block count). */
+int t3d_tsdf_extract_points_view(t3d_tsdf* v, const t3d_frame_view* view_h, int H,
+                                 int W, float depth_max, float weight_threshold,
+                                 float* xyz, float* nrm, uint8_t* rgb,
+                                 int64_t capacity, int64_t* out_n,
+                                 int64_t* out_blocks_h, t3d_stream stream);
+
 /* ------------------------------------------------------------------------- */
 /* K7 — normal estimation (north_star; Open3D estimate_normals KNN, R7).      */
 /* ------------------------------------------------------------------------- */

@@ -39,6 +39,7 @@ def lib():
         _lib.o_tsdf_touch.restype = C.c_int64
         _lib.o_tsdf_num_blocks.restype = C.c_int64
         _lib.o_tsdf_extract.restype = C.c_int64
+        _lib.o_tsdf_extract_view.restype = C.c_int64
         _lib.o_icp_point_to_plane.restype = C.c_int
         _lib.o_num_threads.restype = C.c_int
     return _lib
@@ -212,13 +213,28 @@ class TSDFVolume:
         lib().o_tsdf_export(self._h, _p(keys), _p(tsdf), _p(w), _p(rgb))
         return keys, tsdf, w, rgb
 
-    def extract_points(self, weight_threshold=3.0):
-        cap = max(self.num_blocks * 512 * 3, 1)
+    def extract_points(self, weight_threshold=3.0, view=None):
+        """view = (K(fx,fy,cx,cy), T_cw 3x4|4x4, H, W, depth_max): only blocks visible from that
+        camera (the frame-to-model tracker's target, see o_block_in_view)."""
+        cap = max(self.num_blocks * 96, 1024)
+        q = None
+        if view is not None:
+            K, T, H, W, dmax = view
+            T = np.asarray(T, np.float32)[:3, :4]
+            q = np.ascontiguousarray(np.concatenate([np.asarray(K, np.float32).reshape(4),
+                                                     np.array([W - 1, H - 1, dmax], np.float32),
+                                                     T[:, :3].reshape(9), T[:, 3].reshape(3)]), np.float32)
         while True:
             xyz = np.empty((cap, 3), np.float32)
             nrm = np.empty((cap, 3), np.float32)
             rgb = np.empty((cap, 3), np.uint8)
-            n = lib().o_tsdf_extract(self._h, C.c_float(weight_threshold), _p(xyz), _p(nrm), _p(rgb), C.c_int64(cap))
+            if q is None:
+                n = lib().o_tsdf_extract(self._h, C.c_float(weight_threshold), _p(xyz), _p(nrm), _p(rgb), C.c_int64(cap))
+            else:
+                nsel = C.c_int64(0)
+                n = lib().o_tsdf_extract_view(self._h, C.c_float(weight_threshold), _p(q), _p(xyz), _p(nrm), _p(rgb),
+                                              C.c_int64(cap), C.byref(nsel))
+                self.last_view_blocks = nsel.value
             if n <= cap:
                 return xyz[:n].copy(), nrm[:n].copy(), rgb[:n].copy()
             cap = n

@@ -181,3 +181,58 @@ def test_full_size_properties(ctx):
     assert p.shape[0] > 50_000
     assert float(r.min().item()) > 1.37 - 0.03 and float(r.max().item()) < 1.63 + 0.03
     assert torch.allclose(nrm.norm(dim=1), torch.ones_like(r), atol=1e-4)
+
+
+def test_extract_view_matches_oracle(ctx, oracle):
+    """View-restricted K6 (the tracker's ICP target): same visible-block count and the same
+    multiset of surface points/normals as the oracle's rule (o_block_in_view)."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(6, H, W, step=3)
+    vol = TSDFVolume(0.01, 0.04, block_capacity=80000, ctx=ctx)
+    ov = oracle.TSDFVolume(0.01, 0.04)
+    for d, c, T in fr:
+        vol.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+        ov.integrate(d, c, K, T, 1.0, 5.0)
+    for T, dmax in ((fr[-1][2], 5.0), (fr[0][2], 3.5), (fr[3][2], 5.0)):
+        gp, gn, _, nsel = vol.extract_points_view(K, T, H, W, dmax, 1.0)
+        op, on, _ = ov.extract_points(1.0, view=(K, T, H, W, dmax))
+        assert nsel == ov.last_view_blocks and 0 < nsel < vol.num_blocks
+        assert len(gp) == len(op) and len(gp) > 1000
+        a = np.concatenate([gp.cpu().numpy().view(np.uint32), gn.cpu().numpy().view(np.uint32)], axis=1)
+        b = np.concatenate([op.view(np.uint32), on.view(np.uint32)], axis=1)
+        assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+    # a camera looking away sees nothing
+    Taway = np.array(fr[0][2], np.float64).copy()
+    Taway[:3, :3] = np.diag([1.0, -1.0, -1.0]) @ Taway[:3, :3]
+    Taway[:3, 3] = np.diag([1.0, -1.0, -1.0]) @ Taway[:3, 3] + np.array([0, 0, -50.0])
+    gp, _, _, nsel = vol.extract_points_view(K, Taway, H, W, 5.0, 1.0)
+    assert nsel == 0 and len(gp) == 0
+
+
+def test_frame_to_model_tracker_vs_oracle(ctx, oracle):
+    """cfg-3 loop (ICP + TSDF): GPU tracker vs the CPU restatement (oracle/ref_tracker.py) on the
+    same frames.  north_star tolerance on ICP poses: <= 1e-4 rad / 1e-4 m."""
+    import torch
+    from oracle import ref_tracker
+    from textureless_3d_reconstruction_b200.tracking import FrameToModelTracker
+    H, W = 240, 136
+    fr, K = frames(7, H, W)
+    kw = dict(voxel_size=0.01, sdf_trunc=0.04, depth_max=5.0, icp_subsample=2, icp_max_corr=0.05)
+    gt = FrameToModelTracker(K, H, W, block_capacity=80000, ctx=ctx, **kw)
+    ot = ref_tracker.FrameToModelTracker(K, H, W, **kw)
+    for i, (d, c, T) in enumerate(fr):
+        Tg = gt.add_frame(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), known_pose=T if i == 0 else None)
+        To = ot.add_frame(d, c, known_pose=T if i == 0 else None)
+        E = Tg @ np.linalg.inv(To)
+        ang = np.arccos(np.clip((np.trace(E[:3, :3]) - 1.0) / 2.0, -1.0, 1.0))
+        assert np.linalg.norm(E[:3, 3]) <= 1e-4 and ang <= 1e-4, (i, E)
+        if i > 0:
+            assert gt.icp_log[i].iterations == ot.icp_log[i]["iterations"]
+            assert abs(gt.icp_log[i].fitness - ot.icp_log[i]["fitness"]) < 1e-6
+    # tracked poses stay near the ground truth (textureless tunnel, coarse 240x136 frames)
+    Tgt = np.eye(4)
+    Tgt[:3, :4] = fr[-1][2]
+    assert np.linalg.norm((gt.poses[-1] @ np.linalg.inv(Tgt))[:3, 3]) < 0.05
+    assert gt.volume.num_blocks == ot.volume.num_blocks

@@ -89,6 +89,7 @@ _SIGS = {
     "t3d_tsdf_export_blocks_range": (_I, [_VP, _I, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
+    "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),
     "t3d_icp_point_to_plane": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _I, _D, _D, C.POINTER(IcpResult), _VP]),
     "t3d_icp_linearize": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _VP, _VP, _VP]),

@@ -407,7 +407,7 @@ static int bp_launch(t3d_ctx* ctx, const t3d_backproject_params* q, const BPFram
     ppt = e ? atoi(e) : 8;
     if (ppt != 4 && ppt != 8) ppt = 8;
     const char* m = getenv("T3D_K1_MINB");
-    minb = m ? atoi(m) : 4;
+    minb = m ? atoi(m) : 5;
   }
   const int tile_px = BP_THREADS * ppt;
   p.tiles_per_frame = (p.P + tile_px - 1) / tile_px;

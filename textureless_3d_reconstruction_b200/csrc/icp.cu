@@ -8,6 +8,9 @@
 // equations.  29 doubles (21 upper JtJ + 6 Jtr + sum d^2 + count) are reduced
 // with warp shuffles, then per-CTA partials are summed by one CTA in a fixed
 // order (deterministic).  No tensor cores: this is a gather + reduction.
+// t3d_icp_point_to_plane runs the whole registration in one cooperative
+// persistent kernel (icp_fused_kernel below); t3d_icp_linearize keeps the
+// one-linearisation-per-call form for the multi-GPU all-reduce path.
 #include <math.h>
 
 #include "knn.cuh"
@@ -84,9 +87,9 @@ __global__ void icp_final_kernel(const double* partial, int nblocks, double* out
 }
 
 // ---- host 6x6 helpers -----------------------------------------------------
-double det6(const double* A) {
+__host__ __device__ double det6(const double* A) {
   double M[36];
-  memcpy(M, A, sizeof(M));
+  for (int i = 0; i < 36; ++i) M[i] = A[i];
   double det = 1.0;
   for (int c = 0; c < 6; ++c) {
     int p = c;
@@ -107,7 +110,7 @@ double det6(const double* A) {
 }
 
 // LDL^T solve of the symmetric system A x = b (no pivoting; A is PSD here)
-bool ldlt_solve6(const double* A, const double* b, double* x) {
+__host__ __device__ bool ldlt_solve6(const double* A, const double* b, double* x) {
   double L[36] = {0}, D[6];
   for (int j = 0; j < 6; ++j) {
     double d = A[j * 6 + j];
@@ -136,7 +139,7 @@ bool ldlt_solve6(const double* A, const double* b, double* x) {
   return true;
 }
 
-void mat4_mul(const double* A, const double* B, double* C) {
+__host__ __device__ void mat4_mul(const double* A, const double* B, double* C) {
   double R[16];
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) {
@@ -144,11 +147,11 @@ void mat4_mul(const double* A, const double* B, double* C) {
       for (int k = 0; k < 4; ++k) s += A[i * 4 + k] * B[k * 4 + j];
       R[i * 4 + j] = s;
     }
-  memcpy(C, R, sizeof(R));
+  for (int i = 0; i < 16; ++i) C[i] = R[i];
 }
 
 // x = (alpha, beta, gamma, tx, ty, tz) -> [Rz(gamma) Ry(beta) Rx(alpha) | t]
-void vec6_to_mat4(const double* x, double* M) {
+__host__ __device__ void vec6_to_mat4(const double* x, double* M) {
   const double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]),
                sg = sin(x[2]);
   M[0] = cg * cb; M[1] = cg * sb * sa - sg * ca; M[2] = cg * sb * ca + sg * sa; M[3] = x[3];
@@ -158,7 +161,7 @@ void vec6_to_mat4(const double* x, double* M) {
 }
 
 // solve the normal equations -> update matrix (identity when ill-posed, R8)
-void solve_update(const double* acc, double* U) {
+__host__ __device__ void solve_update(const double* acc, double* U) {
   double A[36], b[6], x[6];
   int q = 0;
   for (int a = 0; a < 6; ++a)
@@ -203,6 +206,460 @@ int linearize(t3d_ctx* ctx, const GridDev& g, const float* src, long long n_src,
 
 }  // namespace
 
+// ===========================================================================
+// Fused registration: hashed target grid (no bounds pass, no sort) + ONE
+// cooperative persistent kernel that runs every ICP iteration on the device:
+// linearise -> grid.sync -> CTA 0 sums the per-CTA partials in a fixed order,
+// checks convergence, solves the 6x6 system in f64 (same det guard + LDL^T as
+// the host code above) and updates T -> grid.sync.  No host round trip per
+// iteration; the host reads one 200-byte result at the end.
+// ===========================================================================
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+struct HGrid {            // cells of size h keyed by floor(p / h) (biased 21-bit pack_key)
+  unsigned long long* keys;
+  unsigned* count;        // points in the cell
+  unsigned* start;        // first sorted position of the cell
+  unsigned* fill;         // scatter cursor
+  unsigned long long mask;
+  float4* xyzi;           // n: {x, y, z, original index as bits}, cell-contiguous
+  float* nrm;             // n*3, same order
+  unsigned* cursor;       // [0] running start allocator, [1] out-of-range flag
+  double inv_h, h;        // cell size h = max_corr / 2: the search covers the 5^3 cells around the query
+  long long n;
+};
+
+// 5x5x5 cell offsets ordered by ring (max-norm) and, inside a ring, by distance:
+// ring 0 = 1 cell, ring 1 = 26, ring 2 = 98.
+__constant__ signed char c_ofs[125][4];
+
+
+__device__ __forceinline__ bool hg_cell(const HGrid& g, double x, double y, double z, int& cx, int& cy, int& cz) {
+  const double fx = floor(x * g.inv_h), fy = floor(y * g.inv_h), fz = floor(z * g.inv_h);
+  if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) return false;
+  cx = (int)fx; cy = (int)fy; cz = (int)fz;
+  return true;
+}
+
+__global__ void hg_count_kernel(const float* __restrict__ tgt, const __grid_constant__ HGrid g) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cx, cy, cz;
+    if (!hg_cell(g, tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2], cx, cy, cz)) { g.cursor[1] = 1; continue; }
+    const unsigned long long key = pack_key(cx, cy, cz);
+    unsigned long long slot = mix64(key) & g.mask;
+    while (true) {
+      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(g.keys + slot));
+      if (k == T3D_KEY_EMPTY) k = atomicCAS(g.keys + slot, T3D_KEY_EMPTY, key);
+      if (k == T3D_KEY_EMPTY || k == key) break;
+      slot = (slot + 1) & g.mask;
+    }
+    atomicAdd(g.count + slot, 1u);
+  }
+}
+
+// cells get their [start, start+count) range from a running cursor: cell order is
+// irrelevant, only contiguity inside a cell matters
+__global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
+  for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s <= g.mask;
+       s += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned c = g.count[s];
+    if (c) g.start[s] = atomicAdd(g.cursor, c);
+  }
+}
+
+__global__ void hg_scatter_kernel(const float* __restrict__ tgt, const float* __restrict__ tgt_nrm,
+                                  const __grid_constant__ HGrid g) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cx, cy, cz;
+    const float x = tgt[3 * i], y = tgt[3 * i + 1], z = tgt[3 * i + 2];
+    if (!hg_cell(g, x, y, z, cx, cy, cz)) continue;
+    const unsigned long long key = pack_key(cx, cy, cz);
+    unsigned long long slot = mix64(key) & g.mask;
+    while (g.keys[slot] != key) slot = (slot + 1) & g.mask;
+    const unsigned pos = g.start[slot] + atomicAdd(g.fill + slot, 1u);
+    g.xyzi[pos] = make_float4(x, y, z, __uint_as_float((unsigned)i));
+    g.nrm[3ll * pos] = tgt_nrm[3 * i]; g.nrm[3ll * pos + 1] = tgt_nrm[3 * i + 1]; g.nrm[3ll * pos + 2] = tgt_nrm[3 * i + 2];
+  }
+}
+
+// Nearest target within sqrt(r2); ties -> lowest original index (as t3d_nn_within).
+// Exact: cells are visited ring by ring around the query's cell; a cell is skipped
+// only if its box is farther than the best distance so far, and the search stops
+// after ring k once best <= (k*h + distance of q to its own cell's faces)^2.
+struct NNState {
+  double best;
+  int bj;
+  unsigned bo;
+};
+
+// squared distance from the query (offset (lx,ly,lz) inside its own cell) to the box of the
+// cell at integer offset (dx,dy,dz)
+__device__ __forceinline__ double hg_box_d2(double h, double lx, double ly, double lz, int dx, int dy, int dz) {
+  const double ax = dx == 0 ? 0.0 : (dx < 0 ? lx + (double)(-dx - 1) * h : (h - lx) + (double)(dx - 1) * h);
+  const double ay = dy == 0 ? 0.0 : (dy < 0 ? ly + (double)(-dy - 1) * h : (h - ly) + (double)(dy - 1) * h);
+  const double az = dz == 0 ? 0.0 : (dz < 0 ? lz + (double)(-dz - 1) * h : (h - lz) + (double)(dz - 1) * h);
+  return ax * ax + ay * ay + az * az;
+}
+
+__device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int cz, double qx, double qy,
+                                             double qz, double r2, NNState& st) {
+  const unsigned long long key = pack_key(cx, cy, cz);
+  unsigned long long slot = mix64(key) & g.mask;
+  unsigned s = 0, e = 0;
+  while (true) {
+    const unsigned long long k = __ldg(g.keys + slot);
+    if (k == key) { s = __ldg(g.start + slot); e = s + __ldg(g.count + slot); break; }
+    if (k == T3D_KEY_EMPTY) break;
+    slot = (slot + 1) & g.mask;
+  }
+  for (unsigned j = s; j < e; ++j) {
+    const float4 t = __ldg(g.xyzi + j);
+    const double ddx = (double)t.x - qx, ddy = (double)t.y - qy, ddz = (double)t.z - qz;
+    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    if (d2 < st.best || (d2 == st.best && d2 <= r2 && __float_as_uint(t.w) < st.bo)) {
+      st.best = d2;
+      st.bj = (int)j;
+      st.bo = __float_as_uint(t.w);
+    }
+  }
+}
+
+// Phase 1 (per thread): rings 0 and 1 (27 cells).  Returns true when the result is final.
+__device__ __forceinline__ bool hg_nn_near(const HGrid& g, double qx, double qy, double qz, double r2,
+                                           int cx, int cy, int cz, double lx, double ly, double lz,
+                                           NNState& st) {
+  const double face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)), fmin(lz, g.h - lz)));
+  int i = 0;
+#pragma unroll 1
+  for (int ring = 0; ring < 2; ++ring) {
+    const int ring_end = ring == 0 ? 1 : 27;
+#pragma unroll 1
+    for (; i < ring_end; ++i) {
+      const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
+      if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
+      hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
+    }
+    const double reach = (double)ring * g.h + face;  // everything closer than this has been seen
+    if (st.bj >= 0 && st.best <= reach * reach) return true;
+  }
+  // ring 2 can only matter if something closer than the current best may hide there
+  const double reach1 = g.h + face;
+  return st.best <= reach1 * reach1;
+}
+
+// Phase 2 (whole warp, one query at a time): the 98 cells of ring 2 are probed 32 at a
+// time — the long tail of queries without a close neighbour costs 4 parallel probe
+// rounds instead of 98 dependent ones.  Ends with a warp arg-min (d2, then index).
+__device__ __forceinline__ void hg_nn_far_warp(const HGrid& g, double qx, double qy, double qz, double r2,
+                                               int cx, int cy, int cz, double lx, double ly, double lz,
+                                               NNState& st, unsigned lane) {
+#pragma unroll 1
+  for (int i = 27 + (int)lane; i < 125; i += 32) {
+    const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
+    if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
+    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, st.best, d);
+    const int oj = __shfl_xor_sync(0xffffffffu, st.bj, d);
+    const unsigned oo = __shfl_xor_sync(0xffffffffu, st.bo, d);
+    if (oj >= 0 && (st.bj < 0 || ob < st.best || (ob == st.best && oo < st.bo))) {
+      st.best = ob; st.bj = oj; st.bo = oo;
+    }
+  }
+}
+
+// 6x6 SPD solve by one warp: lane j < 6 holds column j of A, lane 6 the right-hand side.
+// Gaussian elimination without pivoting (== LDL^T pivots, det = product of pivots), then
+// back substitution; every lane ends with the same x.  Returns false when ill-posed (R8:
+// |det| < 1e-6 or non-finite -> identity update).
+__device__ __forceinline__ bool warp_solve6(const double* acc, double* x, unsigned lane) {
+  double a[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = 0.0;
+    if (lane < 6) {  // A[i][lane] from the packed upper triangle
+      const int r = i < (int)lane ? i : (int)lane, c = i < (int)lane ? (int)lane : i;
+      v = acc[r * 6 - r * (r - 1) / 2 + (c - r)];
+    } else if (lane == 6) {
+      v = -acc[21 + i];
+    }
+    a[i] = v;
+  }
+  double det = 1.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double pk = __shfl_sync(0xffffffffu, a[k], k);
+    det *= pk;
+    if (pk == 0.0 || !isfinite(pk)) ok = false;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = __shfl_sync(0xffffffffu, a[i], k) / pk;
+      a[i] -= f * a[k];
+    }
+  }
+  if (!ok || !isfinite(det) || fabs(det) < 1e-6) return false;
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double sacc = __shfl_sync(0xffffffffu, a[i], 6);
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) sacc -= __shfl_sync(0xffffffffu, a[i], j) * x[j];
+    x[i] = sacc / __shfl_sync(0xffffffffu, a[i], i);
+  }
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) fin = fin && isfinite(x[i]);
+  return fin;
+}
+
+struct IcpState {       // device-resident registration state (also the D2H result record)
+  double T[16];
+  double fitness, rmse;
+  double acc[NACC];     // last linearisation
+  int iterations, converged, done, pad;
+};
+
+__global__ void __launch_bounds__(ICP_THREADS)
+    icp_fused_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
+                     double r2, int max_iter, double rel_fitness, double rel_rmse, IcpState* st,
+                     double* partial /* gridDim.x * NACC */) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s[ICP_THREADS / 32][NACC];
+  __shared__ double s_T[12];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int round = 0;; ++round) {
+    if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<volatile double*>(&st->T[threadIdx.x]);
+    __syncthreads();
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - l; base < n_src;
+         base += (long long)gridDim.x * blockDim.x) {  // warp-uniform trip count
+      const long long i = base + l;
+      const bool valid = i < n_src;
+      double sx = 0.0, sy = 0.0, sz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
+      int cx = 0, cy = 0, cz = 0;
+      NNState nn;
+      nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
+      bool final_ = true;
+      if (valid) {
+        const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+        sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+        sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+        sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
+        if (hg_cell(g, sx, sy, sz, cx, cy, cz)) {
+          lx = sx - (double)cx * g.h; ly = sy - (double)cy * g.h; lz = sz - (double)cz * g.h;
+          final_ = hg_nn_near(g, sx, sy, sz, r2, cx, cy, cz, lx, ly, lz, nn);
+        }
+      }
+      // queries that still need ring 2: the warp serves them one at a time
+      unsigned need = __ballot_sync(0xffffffffu, !final_);
+      while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        NNState q;
+        q.best = __shfl_sync(0xffffffffu, nn.best, L);
+        q.bj = __shfl_sync(0xffffffffu, nn.bj, L);
+        q.bo = __shfl_sync(0xffffffffu, nn.bo, L);
+        hg_nn_far_warp(g, __shfl_sync(0xffffffffu, sx, L), __shfl_sync(0xffffffffu, sy, L),
+                       __shfl_sync(0xffffffffu, sz, L), r2, __shfl_sync(0xffffffffu, cx, L),
+                       __shfl_sync(0xffffffffu, cy, L), __shfl_sync(0xffffffffu, cz, L),
+                       __shfl_sync(0xffffffffu, lx, L), __shfl_sync(0xffffffffu, ly, L),
+                       __shfl_sync(0xffffffffu, lz, L), q, l);
+        if ((int)l == L) nn = q;
+      }
+      const int j = nn.bj;
+      if (!valid || j < 0) continue;
+      const double d2 = nn.best;
+      const float4 tp = g.xyzi[j];
+      const double tx = tp.x, ty = tp.y, tz = tp.z;
+      const double nx = g.nrm[3ll * j], ny = g.nrm[3ll * j + 1], nz = g.nrm[3ll * j + 2];
+      const double r = (sx - tx) * nx + (sy - ty) * ny + (sz - tz) * nz;
+      double J[6];
+      J[0] = sy * nz - sz * ny;
+      J[1] = sz * nx - sx * nz;
+      J[2] = sx * ny - sy * nx;
+      J[3] = nx; J[4] = ny; J[5] = nz;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[q++] += J[a] * J[b];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+      acc[27] += d2;
+      acc[28] += 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k)
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    if (l == 0)
+      for (int k = 0; k < NACC; ++k) s[w][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+      double t = 0.0;
+      for (int ww = 0; ww < ICP_THREADS / 32; ++ww) t += s[ww][threadIdx.x];
+      partial[(long long)blockIdx.x * NACC + threadIdx.x] = t;
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+      // fixed-order final sum (deterministic): warp w sums every 4th CTA partial with 8
+      // independent accumulators (loads in flight), then the four warp sums are combined
+      {
+        const int k = l;
+        double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (k < NACC) {
+          const unsigned nb = gridDim.x;
+          unsigned b = w;
+          for (; b + 28 < nb; b += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] += partial[(long long)(b + 4 * u) * NACC + k];
+          }
+          for (int u = 0; b < nb; b += 4, ++u) a8[u & 7] += partial[(long long)b * NACC + k];
+          s[w][k] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < NACC)
+        st->acc[threadIdx.x] = (s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x]);
+      __syncthreads();
+      if (w == 0) {  // warp 0: convergence bookkeeping (uniform) + warp-parallel 6x6 solve
+        const double cnt = st->acc[28];
+        const double f2 = cnt / (double)n_src;
+        const double e2 = cnt > 0.0 ? sqrt(st->acc[27] / cnt) : 0.0;
+        bool done = false;
+        int converged = 0;
+        if (round > 0 && fabs(st->fitness - f2) < rel_fitness && fabs(st->rmse - e2) < rel_rmse) {
+          converged = 1;
+          done = true;
+        }
+        if (!done && round >= max_iter) done = true;
+        double x[6] = {0, 0, 0, 0, 0, 0};
+        bool solved = false;
+        if (!done) solved = warp_solve6(st->acc, x, l);
+        __syncwarp();
+        if (l == 0) {
+          if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
+          if (converged) st->converged = 1;
+          st->fitness = f2;
+          st->rmse = e2;
+          if (!done && solved) {  // ill-posed -> identity update (R8)
+            double U[16], Tn[16], Tc[16];
+            for (int i = 0; i < 16; ++i) Tc[i] = st->T[i];
+            vec6_to_mat4(x, U);
+            mat4_mul(U, Tc, Tn);
+            for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
+          }
+          st->done = done ? 1 : 0;
+          __threadfence();
+        }
+      }
+    }
+    grid.sync();
+    if (*reinterpret_cast<volatile int*>(&st->done)) break;
+  }
+}
+
+}  // namespace
+
+static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float* tgt, const float* tgt_nrm,
+                     int64_t n_tgt, double max_corr, const double* T0, int max_iter, double rel_fitness,
+                     double rel_rmse, t3d_icp_result* res, cudaStream_t st) {
+  T3D_REQUIRE(n_tgt < (1ll << 31) && n_src < (1ll << 40), "icp: cloud too large");
+  unsigned long long hc = 1024;
+  while (hc < 2ull * (unsigned long long)n_tgt) hc <<= 1;
+  int rc;
+  if ((rc = ctx->scratch[0].reserve(hc * 20)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[1].reserve((size_t)n_tgt * 28 + 64)) != T3D_OK) return rc;
+  static bool ofs_ready = false;
+  if (!ofs_ready) {  // 5^3 offsets sorted by (ring, squared length)
+    signed char h_ofs[125][4];
+    int order[125], key[125];
+    for (int i = 0; i < 125; ++i) {
+      const int dx = i % 5 - 2, dy = (i / 5) % 5 - 2, dz = i / 25 - 2;
+      const int ring = abs(dx) > abs(dy) ? (abs(dx) > abs(dz) ? abs(dx) : abs(dz)) : (abs(dy) > abs(dz) ? abs(dy) : abs(dz));
+      key[i] = ring * 1000 + dx * dx + dy * dy + dz * dz;
+      order[i] = i;
+    }
+    for (int a = 1; a < 125; ++a)  // insertion sort, stable
+      for (int b = a; b > 0 && key[order[b - 1]] > key[order[b]]; --b) { int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+    for (int i = 0; i < 125; ++i) {
+      const int o = order[i];
+      h_ofs[i][0] = (signed char)(o % 5 - 2); h_ofs[i][1] = (signed char)((o / 5) % 5 - 2);
+      h_ofs[i][2] = (signed char)(o / 25 - 2); h_ofs[i][3] = 0;
+    }
+    T3D_CUDA(cudaMemcpyToSymbol(c_ofs, h_ofs, sizeof(h_ofs)));
+    ofs_ready = true;
+  }
+  HGrid g;
+  g.keys = ctx->scratch[0].as<unsigned long long>();
+  g.count = reinterpret_cast<unsigned*>(g.keys + hc);
+  g.start = g.count + hc;
+  g.fill = g.start + hc;
+  g.mask = hc - 1;
+  g.xyzi = ctx->scratch[1].as<float4>();
+  g.nrm = reinterpret_cast<float*>(g.xyzi + n_tgt);
+  g.h = max_corr * 0.5;
+  g.inv_h = 1.0 / g.h;
+  g.n = n_tgt;
+  int nblk = 0;
+  T3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, icp_fused_kernel, ICP_THREADS, 0));
+  if (nblk < 1) nblk = 1;
+  if (nblk > 4) nblk = 4;
+  long long want = (n_src + ICP_THREADS - 1) / ICP_THREADS;
+  int grid = (int)(want < (long long)ctx->num_sms * nblk ? (want > 0 ? want : 1) : (long long)ctx->num_sms * nblk);
+  if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
+  double* partial = ctx->scratch[6].as<double>();
+  IcpState* dst = reinterpret_cast<IcpState*>(partial + (size_t)grid * NACC);
+  if ((rc = ctx->scratch[2].reserve(64)) != T3D_OK) return rc;
+  g.cursor = ctx->scratch[2].as<unsigned>();
+
+  T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
+  T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
+  T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
+  const int bgrid = (int)((n_tgt + 255) / 256 < (long long)ctx->num_sms * 8 ? (n_tgt + 255) / 256 : (long long)ctx->num_sms * 8);
+  hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
+  T3D_LAUNCH_CHECK();
+  hg_alloc_kernel<<<(int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368), 256, 0, st>>>(g);
+  T3D_LAUNCH_CHECK();
+  hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
+  T3D_LAUNCH_CHECK();
+
+  IcpState* hst = reinterpret_cast<IcpState*>(reinterpret_cast<char*>(ctx->pinned) + 2048);
+  memset(hst, 0, sizeof(IcpState));
+  for (int i = 0; i < 16; ++i) hst->T[i] = T0[i];
+  T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
+  double r2 = max_corr * max_corr;
+  long long n_src_ll = n_src;
+  void* args[] = {(void*)&g, (void*)&src, (void*)&n_src_ll, (void*)&r2, (void*)&max_iter,
+                  (void*)&rel_fitness, (void*)&rel_rmse, (void*)&dst, (void*)&partial};
+  T3D_CUDA(cudaLaunchCooperativeKernel((void*)icp_fused_kernel, dim3(grid), dim3(ICP_THREADS), args, 0, st));
+  ctx->launches += 4;
+  T3D_CUDA(cudaMemcpyAsync(hst, dst, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
+  unsigned* hflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + 1024);
+  T3D_CUDA(cudaMemcpyAsync(hflag, g.cursor, 8, cudaMemcpyDeviceToHost, st));
+  T3D_CUDA(cudaStreamSynchronize(st));
+  if (hflag[1]) {
+    t3d_set_error("icp: target coordinates exceed +-2^19 * max_corr_dist");
+    return T3D_E_NUMERIC;
+  }
+  for (int i = 0; i < 16; ++i) res->T[i] = hst->T[i];
+  res->fitness = hst->fitness;
+  res->inlier_rmse = hst->rmse;
+  res->iterations = hst->iterations;
+  res->converged = hst->converged;
+  res->correspondences = (int64_t)hst->acc[28];
+  return T3D_OK;
+}
+
 extern "C" int t3d_icp_linearize(t3d_ctx* ctx, const float* src, int64_t n_src, const float* tgt,
                                  const float* tgt_nrm, int64_t n_tgt, double max_corr_dist,
                                  const double* T_h, double* out27_h, double* out_stats_h,
@@ -238,6 +695,11 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
   if (n_src == 0 || n_tgt == 0) return T3D_OK;
   T3D_REQUIRE(src && tgt && tgt_nrm, "t3d_icp_point_to_plane: null clouds");
   cudaStream_t st = as_stream(stream);
+  static int host_loop = -1;  // debug knob: T3D_ICP_HOSTLOOP=1 -> per-iteration host loop over the sorted grid
+  if (host_loop < 0) host_loop = getenv("T3D_ICP_HOSTLOOP") ? 1 : 0;
+  if (!host_loop)
+    return icp_fused(ctx, src, n_src, tgt, tgt_nrm, n_tgt, max_corr_dist, res->T, max_iter, rel_fitness,
+                     rel_rmse, res, st);
   GridDev g;
   int rc = t3d_grid_build(ctx, tgt, 0, n_tgt, max_corr_dist, &g, st);
   if (rc != T3D_OK) return rc;

@@ -163,30 +163,23 @@ class DepthEnhancedReconstruction:
         ctx = get_context()
         dev = ctx.device
         K4 = (self.K[0, 0], self.K[1, 1], self.K[0, 2], self.K[1, 2])
-        gen = DensePointCloudGenerator(self.intrinsics)
-        vol = TSDFVolume(self.voxel_size, self.sdf_trunc, self.block_capacity, ctx=ctx)
-        T_cw = np.eye(4)
+        h, w = self.images[0].shape[:2]
+        from .tracking import FrameToModelTracker
+        tracker = FrameToModelTracker(K4, h, w, voxel_size=self.voxel_size, sdf_trunc=self.sdf_trunc,
+                                      depth_max=self.depth_max, block_capacity=self.block_capacity,
+                                      icp_subsample=self.icp_subsample, icp_max_corr=self.icp_max_corr, ctx=ctx)
+        vol = tracker.volume
         self.camera_poses, self.icp_log = [], []
         for i, (img, depth) in enumerate(zip(self.images, self.depths)):
             if depth is None:
                 continue
             d = torch.from_numpy(np.ascontiguousarray(depth, np.float32)).to(dev)
             c = torch.from_numpy(np.ascontiguousarray(img, np.uint8)).to(dev)
-            if i > 0:
-                guess = np.asarray(init_poses[i], np.float64) if init_poses is not None else T_cw
-                # model surface (points + normals) from the TSDF, source = this frame's cloud
-                tgt, tgt_n, _ = vol.extract_points(weight_threshold=1.0, with_colors=False)
-                src, _ = gen.depth_to_pointcloud_device(d, c, pose=None, min_depth=0.1, max_depth=self.depth_max,
-                                                        subsample=self.icp_subsample)
-                if tgt.shape[0] > 100 and src.shape[0] > 100:
-                    res = ctx.icp_point_to_plane(src.contiguous(), tgt.contiguous(), tgt_n.contiguous(),
-                                                 self.icp_max_corr, init=np.linalg.inv(guess), max_iter=30)
-                    T_cw = np.linalg.inv(res.transformation)
-                    self.icp_log.append(res)
-                else:
-                    T_cw = guess
-            vol.integrate(d, c, K4, T_cw, depth_scale=1.0, depth_max=self.depth_max)
+            T_cw = tracker.add_frame(d, c, init_pose=None if init_poses is None else init_poses[i])
+            if tracker.icp_log[-1] is not None:
+                self.icp_log.append(tracker.icp_log[-1])
             self.camera_poses.append((T_cw[:3, :3].copy(), T_cw[:3, 3:4].copy()))
+        self.tracker = tracker
         pts, _, cols = vol.extract_points(weight_threshold=1.0, with_normals=False)
         all_points, all_colors = pts.cpu().numpy(), cols.cpu().numpy()
         self.volume = vol

@@ -448,6 +448,38 @@ class TSDFVolume:
             cap = cnt
 
 
+    def extract_points_view(self, K, T_cw, H, W, depth_max=5.0, weight_threshold=1.0, with_normals=True,
+                            with_colors=False, buffers=None):
+        """K6 over the blocks visible from camera (K, T_cw) only — the frame-to-model ICP target.
+        buffers: optional dict reused across calls (grown on demand).  Returns (xyz, nrm, rgb, n_blocks)."""
+        torch = _torch()
+        dev = self.ctx.device
+        arr = (FrameView * 1)()
+        arr[0].depth = None
+        arr[0].bgr = None
+        arr[0].K[:] = np.asarray(K, np.float32).reshape(4).tolist()
+        arr[0].T_cw[:] = np.asarray(T_cw, np.float64)[:3, :4].astype(np.float32).reshape(12).tolist()
+        buffers = buffers if buffers is not None else {}
+        cap = int(buffers.get("cap", 1 << 20))
+        while True:
+            if buffers.get("xyz") is None or buffers["xyz"].shape[0] < cap:
+                buffers["xyz"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+                buffers["nrm"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+                buffers["rgb"] = torch.empty((cap, 3), dtype=torch.uint8, device=dev)
+                buffers["n"] = torch.zeros(1, dtype=torch.int64, device=dev)
+                buffers["cap"] = cap
+            nsel = C.c_int64(0)
+            check(self.lib.t3d_tsdf_extract_points_view(
+                self.handle, arr, int(H), int(W), float(depth_max), float(weight_threshold), _ptr(buffers["xyz"]),
+                _ptr(buffers["nrm"]) if with_normals else None, _ptr(buffers["rgb"]) if with_colors else None,
+                buffers["xyz"].shape[0], _ptr(buffers["n"]), C.byref(nsel), _stream()))
+            cnt = int(buffers["n"].item())
+            if cnt <= buffers["xyz"].shape[0]:
+                return (buffers["xyz"][:cnt], buffers["nrm"][:cnt] if with_normals else None,
+                        buffers["rgb"][:cnt] if with_colors else None, int(nsel.value))
+            cap = int(cnt * 1.25) + 1024
+
+
 def write_ply(path, points, colors=None, normals=None, layout=_lib.PLY_O3D_BINARY):
     """Host-side PLY writer through the C ABI (K9).  points: (N,3) f32|f64 NumPy."""
     lib = _lib.load()
