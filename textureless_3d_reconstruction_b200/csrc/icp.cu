@@ -8,8 +8,8 @@
 // equations.  29 doubles (21 upper JtJ + 6 Jtr + sum d^2 + count) are reduced
 // with warp shuffles, then per-CTA partials are summed by one CTA in a fixed
 // order (deterministic).  No tensor cores: this is a gather + reduction.
-// t3d_icp_point_to_plane runs the whole registration in one cooperative
-// persistent kernel (icp_fused_kernel below); t3d_icp_linearize keeps the
+// t3d_icp_point_to_plane keeps the whole registration on the device
+// (icp_nn_kernel / icp_acc_kernel below); t3d_icp_linearize keeps the
 // one-linearisation-per-call form for the multi-GPU all-reduce path.
 #include <math.h>
 
@@ -207,15 +207,13 @@ int linearize(t3d_ctx* ctx, const GridDev& g, const float* src, long long n_src,
 }  // namespace
 
 // ===========================================================================
-// Fused registration: hashed target grid (no bounds pass, no sort) + ONE
-// cooperative persistent kernel that runs every ICP iteration on the device:
-// linearise -> grid.sync -> CTA 0 sums the per-CTA partials in a fixed order,
-// checks convergence, solves the 6x6 system in f64 (same det guard + LDL^T as
-// the host code above) and updates T -> grid.sync.  No host round trip per
-// iteration; the host reads one 200-byte result at the end.
+// Device-resident registration: hashed target grid (no bounds pass, no sort) and
+// a registration state that lives in HBM.  Every iteration is two launches
+// (correspondences; accumulate + reduce + 6x6 solve by the last CTA) that turn
+// into no-ops once the state says "done", so the host enqueues a handful of
+// iterations at a time and reads one small result record back — no host round
+// trip, H2D pose upload or D2H reduction per iteration.
 // ===========================================================================
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -224,6 +222,9 @@ struct HGrid {            // cells of size h keyed by floor(p / h) (biased 21-bi
   unsigned* count;        // points in the cell
   unsigned* start;        // first sorted position of the cell
   unsigned* fill;         // scatter cursor
+  unsigned long long* near_keys;  // set of coarse cells (2h = max_corr) with a target within one coarse
+                                  // cell in every direction: a query whose coarse cell is absent has no
+                                  // correspondence — decided by ONE probe instead of 125
   unsigned long long mask;
   float4* xyzi;           // n: {x, y, z, original index as bits}, cell-contiguous
   float* nrm;             // n*3, same order
@@ -267,7 +268,38 @@ __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
   for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s <= g.mask;
        s += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned c = g.count[s];
-    if (c) g.start[s] = atomicAdd(g.cursor, c);
+    if (!c) continue;
+    g.start[s] = atomicAdd(g.cursor, c);
+    // mark the 27 coarse cells around this fine cell's coarse cell
+    int fx, fy, fz;
+    unpack_key(g.keys[s], fx, fy, fz);
+    const int qx = fx >> 1, qy = fy >> 1, qz = fz >> 1;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const unsigned long long key = pack_key(qx + dx, qy + dy, qz + dz);
+          unsigned long long slot = mix64(key) & g.mask;
+          while (true) {
+            unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(g.near_keys + slot));
+            if (k == key) break;
+            if (k == T3D_KEY_EMPTY) {
+              k = atomicCAS(g.near_keys + slot, T3D_KEY_EMPTY, key);
+              if (k == T3D_KEY_EMPTY || k == key) break;
+            }
+            slot = (slot + 1) & g.mask;
+          }
+        }
+  }
+}
+
+__device__ __forceinline__ bool hg_near_target(const HGrid& g, int cx, int cy, int cz) {
+  const unsigned long long key = pack_key(cx >> 1, cy >> 1, cz >> 1);
+  unsigned long long slot = mix64(key) & g.mask;
+  while (true) {
+    const unsigned long long k = __ldg(g.near_keys + slot);
+    if (k == key) return true;
+    if (k == T3D_KEY_EMPTY) return false;
+    slot = (slot + 1) & g.mask;
   }
 }
 
@@ -330,24 +362,31 @@ __device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int
 }
 
 // Phase 1 (per thread): rings 0 and 1 (27 cells).  Returns true when the result is final.
+// The 8 cells of the query's octant (its own cell and the neighbours on the side of the
+// cell the query sits in) are probed first: with h ~ 2-3 surface samples they almost
+// always hold the nearest neighbour, after which the other 19 cells are rejected by the
+// box-distance test alone (no memory access).  Every lane of a warp runs the same 8-probe
+// sequence, so the octant pass is divergence-free.
 __device__ __forceinline__ bool hg_nn_near(const HGrid& g, double qx, double qy, double qz, double r2,
                                            int cx, int cy, int cz, double lx, double ly, double lz,
                                            NNState& st) {
   const double face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)), fmin(lz, g.h - lz)));
-  int i = 0;
+  const double hh = 0.5 * g.h;
+  const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
 #pragma unroll 1
-  for (int ring = 0; ring < 2; ++ring) {
-    const int ring_end = ring == 0 ? 1 : 27;
-#pragma unroll 1
-    for (; i < ring_end; ++i) {
-      const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
-      if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
-      hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
-    }
-    const double reach = (double)ring * g.h + face;  // everything closer than this has been seen
-    if (st.bj >= 0 && st.best <= reach * reach) return true;
+  for (int o = 0; o < 8; ++o) {
+    const int dx = (o & 1) ? ox : 0, dy = (o & 2) ? oy : 0, dz = (o & 4) ? oz : 0;
+    if (o != 0 && hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
+    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
   }
-  // ring 2 can only matter if something closer than the current best may hide there
+#pragma unroll 1
+  for (int i = 1; i < 27; ++i) {
+    const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
+    if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
+    if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
+    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
+  }
+  // after rings 0+1 everything closer than h + face has been seen
   const double reach1 = g.h + face;
   return st.best <= reach1 * reach1;
 }
@@ -423,148 +462,196 @@ struct IcpState {       // device-resident registration state (also the D2H resu
   double T[16];
   double fitness, rmse;
   double acc[NACC];     // last linearisation
-  int iterations, converged, done, pad;
+  int iterations, converged, done, round;
+  unsigned ticket, pad;
 };
 
+// One linearisation = two launches, both of which return at once when the
+// registration has already finished (st->done), so the host can enqueue several
+// rounds without a round trip per iteration:
+//   icp_nn_kernel   correspondences only — small register footprint, many resident
+//                   warps to hide the latency of the hash probes and candidate loads;
+//   icp_acc_kernel  J^T J / J^T r accumulation from the stored correspondences; the
+//                   last CTA to finish sums the per-CTA partials in blockIdx order
+//                   (deterministic), checks convergence and solves the 6x6 system.
+constexpr int NN_THREADS = 256;
+
+__global__ void __launch_bounds__(NN_THREADS, 4)
+    icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
+                  double r2, const IcpState* st, int* __restrict__ corr, double* __restrict__ corr_d2) {
+  if (*reinterpret_cast<const volatile int*>(&st->done)) return;
+  __shared__ double s_T[12];
+  if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
+  __syncthreads();
+  const unsigned l = lane_id();
+  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - l; base < n_src;
+       base += (long long)gridDim.x * blockDim.x) {  // warp-uniform trip count
+    const long long i = base + l;
+    const bool valid = i < n_src;
+    double sx = 0.0, sy = 0.0, sz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
+    int cx = 0, cy = 0, cz = 0;
+    NNState nn;
+    nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
+    bool final_ = true;
+    if (valid) {
+      const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+      sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+      sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+      sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
+      if (hg_cell(g, sx, sy, sz, cx, cy, cz) && hg_near_target(g, cx, cy, cz)) {
+        lx = sx - (double)cx * g.h; ly = sy - (double)cy * g.h; lz = sz - (double)cz * g.h;
+        final_ = hg_nn_near(g, sx, sy, sz, r2, cx, cy, cz, lx, ly, lz, nn);
+      }
+    }
+    // queries that still need ring 2.  Few per warp: the warp serves them one at a time,
+    // 32 cells per step.  Many (spatially coherent misses): every lane walks its own ring 2.
+    unsigned need = __ballot_sync(0xffffffffu, !final_);
+    if (__popc(need) > 6) {
+      if (!final_) {
+#pragma unroll 1
+        for (int c = 27; c < 125; ++c) {
+          const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
+          if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > nn.best) continue;
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
+        }
+      }
+      need = 0;
+    }
+    while (need) {
+      const int L = __ffs(need) - 1;
+      need &= need - 1;
+      NNState q;
+      q.best = __shfl_sync(0xffffffffu, nn.best, L);
+      q.bj = __shfl_sync(0xffffffffu, nn.bj, L);
+      q.bo = __shfl_sync(0xffffffffu, nn.bo, L);
+      hg_nn_far_warp(g, __shfl_sync(0xffffffffu, sx, L), __shfl_sync(0xffffffffu, sy, L),
+                     __shfl_sync(0xffffffffu, sz, L), r2, __shfl_sync(0xffffffffu, cx, L),
+                     __shfl_sync(0xffffffffu, cy, L), __shfl_sync(0xffffffffu, cz, L),
+                     __shfl_sync(0xffffffffu, lx, L), __shfl_sync(0xffffffffu, ly, L),
+                     __shfl_sync(0xffffffffu, lz, L), q, l);
+      if ((int)l == L) nn = q;
+    }
+    if (valid) {
+      corr[i] = nn.bj;
+      corr_d2[i] = nn.best;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ICP_THREADS)
-    icp_fused_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
-                     double r2, int max_iter, double rel_fitness, double rel_rmse, IcpState* st,
-                     double* partial /* gridDim.x * NACC */) {
-  cg::grid_group grid = cg::this_grid();
+    icp_acc_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
+                   int max_iter, double rel_fitness, double rel_rmse, IcpState* st,
+                   const int* __restrict__ corr, const double* __restrict__ corr_d2,
+                   double* partial /* gridDim.x * NACC */) {
+  if (*reinterpret_cast<volatile int*>(&st->done)) return;
   __shared__ double s[ICP_THREADS / 32][NACC];
   __shared__ double s_T[12];
+  __shared__ unsigned s_last;
+  if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<volatile double*>(&st->T[threadIdx.x]);
+  __syncthreads();
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int round = 0;; ++round) {
-    if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<volatile double*>(&st->T[threadIdx.x]);
-    __syncthreads();
-    double acc[NACC];
+  double acc[NACC];
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - l; base < n_src;
-         base += (long long)gridDim.x * blockDim.x) {  // warp-uniform trip count
-      const long long i = base + l;
-      const bool valid = i < n_src;
-      double sx = 0.0, sy = 0.0, sz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
-      int cx = 0, cy = 0, cz = 0;
-      NNState nn;
-      nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
-      bool final_ = true;
-      if (valid) {
-        const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
-        sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
-        sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
-        sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
-        if (hg_cell(g, sx, sy, sz, cx, cy, cz)) {
-          lx = sx - (double)cx * g.h; ly = sy - (double)cy * g.h; lz = sz - (double)cz * g.h;
-          final_ = hg_nn_near(g, sx, sy, sz, r2, cx, cy, cz, lx, ly, lz, nn);
-        }
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_src;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = corr[i];
+    if (j < 0) continue;
+    const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+    const double sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+    const double sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+    const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
+    const float4 tp = g.xyzi[j];
+    const double tx = tp.x, ty = tp.y, tz = tp.z;
+    const double nx = g.nrm[3ll * j], ny = g.nrm[3ll * j + 1], nz = g.nrm[3ll * j + 2];
+    const double r = (sx - tx) * nx + (sy - ty) * ny + (sz - tz) * nz;
+    double J[6];
+    J[0] = sy * nz - sz * ny;
+    J[1] = sz * nx - sx * nz;
+    J[2] = sx * ny - sy * nx;
+    J[3] = nx; J[4] = ny; J[5] = nz;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[q++] += J[a] * J[b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+    acc[27] += corr_d2[i];
+    acc[28] += 1.0;
+  }
+#pragma unroll
+  for (int k = 0; k < NACC; ++k)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+  if (l == 0)
+    for (int k = 0; k < NACC; ++k) s[w][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double t = 0.0;
+    for (int ww = 0; ww < ICP_THREADS / 32; ++ww) t += s[ww][threadIdx.x];
+    partial[(long long)blockIdx.x * NACC + threadIdx.x] = t;
+  }
+  // last CTA to arrive finishes the round
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {  // fixed-order final sum: warp w takes every 4th partial with 8 independent accumulators
+    const int k = l;
+    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (k < NACC) {
+      const unsigned nb = gridDim.x;
+      unsigned b = w;
+      for (; b + 28 < nb; b += 32) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          a8[u] += *reinterpret_cast<volatile double*>(&partial[(long long)(b + 4 * u) * NACC + k]);
       }
-      // queries that still need ring 2: the warp serves them one at a time
-      unsigned need = __ballot_sync(0xffffffffu, !final_);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        NNState q;
-        q.best = __shfl_sync(0xffffffffu, nn.best, L);
-        q.bj = __shfl_sync(0xffffffffu, nn.bj, L);
-        q.bo = __shfl_sync(0xffffffffu, nn.bo, L);
-        hg_nn_far_warp(g, __shfl_sync(0xffffffffu, sx, L), __shfl_sync(0xffffffffu, sy, L),
-                       __shfl_sync(0xffffffffu, sz, L), r2, __shfl_sync(0xffffffffu, cx, L),
-                       __shfl_sync(0xffffffffu, cy, L), __shfl_sync(0xffffffffu, cz, L),
-                       __shfl_sync(0xffffffffu, lx, L), __shfl_sync(0xffffffffu, ly, L),
-                       __shfl_sync(0xffffffffu, lz, L), q, l);
-        if ((int)l == L) nn = q;
-      }
-      const int j = nn.bj;
-      if (!valid || j < 0) continue;
-      const double d2 = nn.best;
-      const float4 tp = g.xyzi[j];
-      const double tx = tp.x, ty = tp.y, tz = tp.z;
-      const double nx = g.nrm[3ll * j], ny = g.nrm[3ll * j + 1], nz = g.nrm[3ll * j + 2];
-      const double r = (sx - tx) * nx + (sy - ty) * ny + (sz - tz) * nz;
-      double J[6];
-      J[0] = sy * nz - sz * ny;
-      J[1] = sz * nx - sx * nz;
-      J[2] = sx * ny - sy * nx;
-      J[3] = nx; J[4] = ny; J[5] = nz;
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[q++] += J[a] * J[b];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
-      acc[27] += d2;
-      acc[28] += 1.0;
+      for (int u = 0; b < nb; b += 4, ++u)
+        a8[u & 7] += *reinterpret_cast<volatile double*>(&partial[(long long)b * NACC + k]);
+      s[w][k] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
     }
-#pragma unroll
-    for (int k = 0; k < NACC; ++k)
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
-    if (l == 0)
-      for (int k = 0; k < NACC; ++k) s[w][k] = acc[k];
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-      double t = 0.0;
-      for (int ww = 0; ww < ICP_THREADS / 32; ++ww) t += s[ww][threadIdx.x];
-      partial[(long long)blockIdx.x * NACC + threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC)
+    st->acc[threadIdx.x] = (s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x]);
+  __syncthreads();
+  if (w == 0) {  // convergence bookkeeping (uniform across the warp) + warp-parallel 6x6 solve
+    const int round = st->round;
+    const double cnt = st->acc[28];
+    const double f2 = cnt / (double)n_src;
+    const double e2 = cnt > 0.0 ? sqrt(st->acc[27] / cnt) : 0.0;
+    bool done = false;
+    int converged = 0;
+    if (round > 0 && fabs(st->fitness - f2) < rel_fitness && fabs(st->rmse - e2) < rel_rmse) {
+      converged = 1;
+      done = true;
     }
-    grid.sync();
-    if (blockIdx.x == 0) {
-      // fixed-order final sum (deterministic): warp w sums every 4th CTA partial with 8
-      // independent accumulators (loads in flight), then the four warp sums are combined
-      {
-        const int k = l;
-        double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (k < NACC) {
-          const unsigned nb = gridDim.x;
-          unsigned b = w;
-          for (; b + 28 < nb; b += 32) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a8[u] += partial[(long long)(b + 4 * u) * NACC + k];
-          }
-          for (int u = 0; b < nb; b += 4, ++u) a8[u & 7] += partial[(long long)b * NACC + k];
-          s[w][k] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-        }
+    if (!done && round >= max_iter) done = true;
+    double x[6] = {0, 0, 0, 0, 0, 0};
+    bool solved = false;
+    if (!done) solved = warp_solve6(st->acc, x, l);
+    __syncwarp();
+    if (l == 0) {
+      if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
+      if (converged) st->converged = 1;
+      st->fitness = f2;
+      st->rmse = e2;
+      if (!done && solved) {  // ill-posed -> identity update (R8)
+        double U[16], Tn[16], Tc[16];
+        for (int i = 0; i < 16; ++i) Tc[i] = st->T[i];
+        vec6_to_mat4(x, U);
+        mat4_mul(U, Tc, Tn);
+        for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
       }
-      __syncthreads();
-      if (threadIdx.x < NACC)
-        st->acc[threadIdx.x] = (s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x]);
-      __syncthreads();
-      if (w == 0) {  // warp 0: convergence bookkeeping (uniform) + warp-parallel 6x6 solve
-        const double cnt = st->acc[28];
-        const double f2 = cnt / (double)n_src;
-        const double e2 = cnt > 0.0 ? sqrt(st->acc[27] / cnt) : 0.0;
-        bool done = false;
-        int converged = 0;
-        if (round > 0 && fabs(st->fitness - f2) < rel_fitness && fabs(st->rmse - e2) < rel_rmse) {
-          converged = 1;
-          done = true;
-        }
-        if (!done && round >= max_iter) done = true;
-        double x[6] = {0, 0, 0, 0, 0, 0};
-        bool solved = false;
-        if (!done) solved = warp_solve6(st->acc, x, l);
-        __syncwarp();
-        if (l == 0) {
-          if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
-          if (converged) st->converged = 1;
-          st->fitness = f2;
-          st->rmse = e2;
-          if (!done && solved) {  // ill-posed -> identity update (R8)
-            double U[16], Tn[16], Tc[16];
-            for (int i = 0; i < 16; ++i) Tc[i] = st->T[i];
-            vec6_to_mat4(x, U);
-            mat4_mul(U, Tc, Tn);
-            for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
-          }
-          st->done = done ? 1 : 0;
-          __threadfence();
-        }
-      }
+      st->round = round + 1;
+      st->ticket = 0;
+      __threadfence();
+      st->done = done ? 1 : 0;
     }
-    grid.sync();
-    if (*reinterpret_cast<volatile int*>(&st->done)) break;
   }
 }
 
@@ -577,7 +664,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   unsigned long long hc = 1024;
   while (hc < 2ull * (unsigned long long)n_tgt) hc <<= 1;
   int rc;
-  if ((rc = ctx->scratch[0].reserve(hc * 20)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[0].reserve(hc * 28)) != T3D_OK) return rc;
   if ((rc = ctx->scratch[1].reserve((size_t)n_tgt * 28 + 64)) != T3D_OK) return rc;
   static bool ofs_ready = false;
   if (!ofs_ready) {  // 5^3 offsets sorted by (ring, squared length)
@@ -604,26 +691,30 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   g.count = reinterpret_cast<unsigned*>(g.keys + hc);
   g.start = g.count + hc;
   g.fill = g.start + hc;
+  g.near_keys = reinterpret_cast<unsigned long long*>(g.fill + hc);
   g.mask = hc - 1;
   g.xyzi = ctx->scratch[1].as<float4>();
   g.nrm = reinterpret_cast<float*>(g.xyzi + n_tgt);
   g.h = max_corr * 0.5;
   g.inv_h = 1.0 / g.h;
   g.n = n_tgt;
-  int nblk = 0;
-  T3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, icp_fused_kernel, ICP_THREADS, 0));
-  if (nblk < 1) nblk = 1;
-  if (nblk > 4) nblk = 4;
-  long long want = (n_src + ICP_THREADS - 1) / ICP_THREADS;
-  int grid = (int)(want < (long long)ctx->num_sms * nblk ? (want > 0 ? want : 1) : (long long)ctx->num_sms * nblk);
-  if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
+  const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
+  const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * 4 ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * 4);
+  const long long want_nn = (n_src + NN_THREADS - 1) / NN_THREADS;
+  const int grid_nn = (int)(want_nn < (long long)ctx->num_sms * 8 ? (want_nn > 0 ? want_nn : 1) : (long long)ctx->num_sms * 8);
+  if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid_acc * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
   double* partial = ctx->scratch[6].as<double>();
-  IcpState* dst = reinterpret_cast<IcpState*>(partial + (size_t)grid * NACC);
+  IcpState* dst = reinterpret_cast<IcpState*>(partial + (size_t)grid_acc * NACC);
   if ((rc = ctx->scratch[2].reserve(64)) != T3D_OK) return rc;
   g.cursor = ctx->scratch[2].as<unsigned>();
+  if ((rc = ctx->scratch[3].reserve((size_t)n_src * 4)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[4].reserve((size_t)n_src * 8)) != T3D_OK) return rc;
+  int* corr = ctx->scratch[3].as<int>();
+  double* corr_d2 = ctx->scratch[4].as<double>();
 
   T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
   T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
+  T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 8, st));
   T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
   const int bgrid = (int)((n_tgt + 255) / 256 < (long long)ctx->num_sms * 8 ? (n_tgt + 255) / 256 : (long long)ctx->num_sms * 8);
   hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
@@ -632,21 +723,35 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   T3D_LAUNCH_CHECK();
   hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
   T3D_LAUNCH_CHECK();
+  ctx->launches += 3;
 
   IcpState* hst = reinterpret_cast<IcpState*>(reinterpret_cast<char*>(ctx->pinned) + 2048);
+  unsigned* hflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + 1024);
   memset(hst, 0, sizeof(IcpState));
   for (int i = 0; i < 16; ++i) hst->T[i] = T0[i];
   T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
-  double r2 = max_corr * max_corr;
-  long long n_src_ll = n_src;
-  void* args[] = {(void*)&g, (void*)&src, (void*)&n_src_ll, (void*)&r2, (void*)&max_iter,
-                  (void*)&rel_fitness, (void*)&rel_rmse, (void*)&dst, (void*)&partial};
-  T3D_CUDA(cudaLaunchCooperativeKernel((void*)icp_fused_kernel, dim3(grid), dim3(ICP_THREADS), args, 0, st));
-  ctx->launches += 4;
-  T3D_CUDA(cudaMemcpyAsync(hst, dst, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
-  unsigned* hflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + 1024);
-  T3D_CUDA(cudaMemcpyAsync(hflag, g.cursor, 8, cudaMemcpyDeviceToHost, st));
-  T3D_CUDA(cudaStreamSynchronize(st));
+  const double r2 = max_corr * max_corr;
+  // rounds needed: at most max_iter + 1.  Enqueue speculatively (finished rounds are no-op
+  // launches), read the state back, continue only if the registration is still running.
+  int enqueued = 0;
+  int chunk = 6;
+  while (true) {
+    int n = max_iter + 1 - enqueued;
+    if (n > chunk) n = chunk;
+    for (int r = 0; r < n; ++r) {
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, r2, dst, corr, corr_d2);
+      icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, max_iter, rel_fitness,
+                                                        rel_rmse, dst, corr, corr_d2, partial);
+    }
+    T3D_LAUNCH_CHECK();
+    ctx->launches += 2 * n;
+    enqueued += n;
+    T3D_CUDA(cudaMemcpyAsync(hst, dst, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
+    T3D_CUDA(cudaMemcpyAsync(hflag, g.cursor, 8, cudaMemcpyDeviceToHost, st));
+    T3D_CUDA(cudaStreamSynchronize(st));
+    if (hst->done || enqueued >= max_iter + 1) break;
+    chunk = 8;
+  }
   if (hflag[1]) {
     t3d_set_error("icp: target coordinates exceed +-2^19 * max_corr_dist");
     return T3D_E_NUMERIC;
