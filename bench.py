@@ -221,6 +221,8 @@ def run_ours(args):
         from textureless_3d_reconstruction_b200.distributed import BlockRouter
         router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
 
+    route_events = []
+
     def step():
         vol.reset()
         if args.serial_batches:
@@ -229,7 +231,11 @@ def run_ours(args):
         else:
             vol.integrate_sequence(views, F, H, W, B, False, 1.0, DEPTH_MAX)
         if router is not None:
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
             router.route()
+            r1.record()
+            route_events.append((r0, r1))
 
     def barrier():
         if world > 1:
@@ -239,6 +245,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    route_events.clear()
 
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local)
@@ -314,6 +321,11 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "blocks_per_gpu": int(nblocks), "batch_frames": B,
         }
+        if router is not None:
+            line["routing"] = {"blocks_sent_rank0": router.last_sent, "blocks_received_rank0": router.last_received,
+                               "bytes_sent_rank0": router.last_sent * 4 * router.RECORD,
+                               "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
+                               "collective": "NCCL all_to_all_single (counts) + all_to_all_single (10 KiB block records)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

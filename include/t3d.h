@@ -233,11 +233,36 @@ int t3d_tsdf_export_blocks_range(t3d_tsdf* v, int axis, int32_t lo, int32_t hi,
                                  int32_t* keys, float* tsdf, float* weight,
                                  float* rgb, int64_t capacity, int64_t* out_b,
                                  t3d_stream stream);
+/* Complement of the above: blocks whose key[axis] is NOT in [lo, hi) — everything a
+ * rank does not own, in one call.  If capacity is too small the call fails with
+ * T3D_E_CAPACITY but *out_b still holds the required count. */
+int t3d_tsdf_export_blocks_outside(t3d_tsdf* v, int axis, int32_t lo, int32_t hi,
+                                   int32_t* keys, float* tsdf, float* weight,
+                                   float* rgb, int64_t capacity, int64_t* out_b,
+                                   t3d_stream stream);
 /* Merge partial blocks into the volume (multi-GPU owner reduce):
  * w' = w_a + w_b, tsdf' = (w_a*tsdf_a + w_b*tsdf_b)/w', same for rgb. */
 int t3d_tsdf_merge_blocks(t3d_tsdf* v, const int32_t* keys, const float* tsdf,
                           const float* weight, const float* rgb, int64_t b,
                           t3d_stream stream);
+
+/* Multi-GPU block routing in wire format (owner(key) = clamp(floor(key[axis] /
+ * slab_blocks), 0, world-1)).  A record is 2564 f32 words = 10 256 B:
+ *   [kx ky kz owner (int32 bits) | tsdf x512 | weight x512 | rgb x1536 voxel-major].
+ * 1. t3d_tsdf_route_counts: counts[d] = number of blocks owned by rank d != self (device).
+ * 2. t3d_tsdf_route_export: writes every non-owned block as a record at row
+ *    dst_base[owner] + k (dst_base = exclusive scan of counts), i.e. grouped by destination —
+ *    directly usable as the send buffer of a variable-size all-to-all.
+ * 3. t3d_tsdf_merge_records: merges received records (keys unique within one call) with
+ *    the t3d_tsdf_merge_blocks rule.
+ * All three are asynchronous (the block count is read on the device). */
+int t3d_tsdf_route_counts(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
+                          int self_rank, int32_t* counts, t3d_stream stream);
+int t3d_tsdf_route_export(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
+                          int self_rank, const int32_t* dst_base, int32_t* dst_fill,
+                          float* records, t3d_stream stream);
+int t3d_tsdf_merge_records(t3d_tsdf* v, const float* records, int64_t b,
+                           t3d_stream stream);
 
 /* K6: surface points (R6).  xyz/nrm: cap*3 f32; rgb: cap*3 u8 (nullable
  * nrm/rgb).  out_n device int64.  Order: deterministic only as a set. */

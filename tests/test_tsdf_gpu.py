@@ -236,3 +236,46 @@ def test_frame_to_model_tracker_vs_oracle(ctx, oracle):
     Tgt[:3, :4] = fr[-1][2]
     assert np.linalg.norm((gt.poses[-1] @ np.linalg.inv(Tgt))[:3, 3]) < 0.05
     assert gt.volume.num_blocks == ot.volume.num_blocks
+
+
+def test_route_records_round_trip(ctx):
+    """Wire-record routing (t3d_tsdf_route_counts / route_export / merge_records) on one GPU:
+    records grouped by owner carry exactly the non-owned blocks, and merging them equals the
+    export_blocks_range + merge_blocks path bit for bit (same weighted-mean rule)."""
+    import torch
+    from textureless_3d_reconstruction_b200.distributed import block_owner_range, owner_of
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(6, H, W, step=2)
+    src = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    for d, c, T in fr:
+        src.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    keys_all = src.export_blocks()[0].cpu().numpy()
+    world, rank, axis = 3, 1, 2
+    slab = max(1, (int(keys_all[:, axis].max()) - int(keys_all[:, axis].min())) // 3)
+    counts = src.route_counts(axis, slab, world, rank)
+    own = owner_of(keys_all[:, axis].astype(np.int64), world, slab)
+    expect = np.bincount(own[own != rank], minlength=world)
+    assert counts.cpu().numpy().tolist() == expect.tolist() and expect.sum() > 100
+    rec = src.route_export(axis, slab, world, rank, counts)
+    assert rec.shape == (int(expect.sum()), 2564)
+    rk = rec[:, :4].contiguous().view(torch.int32).cpu().numpy()
+    assert np.array_equal(rk[:, 3], np.sort(rk[:, 3]))                       # grouped by destination
+    assert np.array_equal(rk[:, 3], owner_of(rk[:, axis].astype(np.int64), world, slab))
+    lo, hi = block_owner_range(rank, world, slab)
+    assert key_rows(rk[:, :3]) == key_rows(keys_all[(keys_all[:, axis] < lo) | (keys_all[:, axis] >= hi)])
+    # merging the records into a volume that already holds overlapping data == merge_blocks
+    a = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    b = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    for vol in (a, b):
+        for d, c, T in fr[:2]:
+            vol.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    a.merge_records(rec.contiguous())
+    ok, ot, ow, oc = src.export_blocks_outside(axis, lo, hi)
+    b.merge_blocks(ok.contiguous(), ot.contiguous(), ow.contiguous(), oc.contiguous())
+    ga = by_key(*[x.cpu().numpy() for x in a.export_blocks()])
+    gb = by_key(*[x.cpu().numpy() for x in b.export_blocks()])
+    assert a.num_blocks == b.num_blocks
+    for x, y in zip(ga, gb):
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
+                              y.view(np.uint32) if y.dtype == np.float32 else y)

@@ -87,6 +87,10 @@ _SIGS = {
     "t3d_tsdf_get_profile": (_I, [_VP, _VP, _VP]),
     "t3d_tsdf_export_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_export_blocks_range": (_I, [_VP, _I, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
+    "t3d_tsdf_export_blocks_outside": (_I, [_VP, _I, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
+    "t3d_tsdf_route_counts": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP]),
+    "t3d_tsdf_route_export": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _VP, _VP]),
+    "t3d_tsdf_merge_records": (_I, [_VP, _VP, _I64, _VP]),
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),

@@ -5,8 +5,8 @@ torch.distributed (NCCL over NVLink/NVSwitch) only where data really has to move
 * TSDF volume: split spatially by voxel-block ownership.  The camera advances along
   +z, so ownership is the z-slab of the block key: owner(zb) = clamp(zb // slab_blocks).
   After a rank has fused its frames, blocks it touched but does not own (the ~5 m of
-  look-ahead past its last camera) are routed to their owner with one variable-size
-  all_to_all and merged there as weighted means (running averages with unit weights
+  look-ahead past its last camera) are exported once, packed into 10 KiB records sorted
+  by owner, routed with one variable-size all_to_all and merged there as weighted means (running averages with unit weights
   are mergeable: w = wa + wb, tsdf = (wa*ta + wb*tb) / w);
 * ICP: source points sharded, per-iteration all_reduce of the 29 normal-equation sums.
 
@@ -50,51 +50,88 @@ class BlockRouter:
         self.last_sent = 0
         self.last_received = 0
 
+    RECORD = 4 + 512 + 512 + 1536   # f32 words per block on the wire: key(3)+pad | tsdf | weight | rgb
+
+    def _export_non_owned(self):
+        lo, hi = block_owner_range(self.rank, self.world, self.slab_blocks)
+        if hasattr(self.vol, "export_blocks_outside"):
+            return self.vol.export_blocks_outside(self.AXIS, lo, hi)
+        import torch
+        below = self.vol.export_blocks_range(self.AXIS, -(1 << 30), lo)
+        above = self.vol.export_blocks_range(self.AXIS, hi, 1 << 30)
+        return tuple(torch.cat([a, b]) for a, b in zip(below, above))
+
     def route(self):
+        """One export of everything this rank does not own, one packed record per block
+        (10 256 B), sorted by owner; one all_to_all for the counts and one for the
+        records; owners merge what they receive, one source rank at a time (a block can
+        arrive from several ranks, and merge_blocks needs unique keys per call)."""
         import torch
         import torch.distributed as dist
         world, rank = self.world, self.rank
         if world == 1:
             return 0
-        parts = []
-        for d in range(world):
-            if d == rank:
-                parts.append(None)
-                continue
-            lo, hi = block_owner_range(d, world, self.slab_blocks)
-            parts.append(self.vol.export_blocks_range(self.AXIS, lo, hi))
-        some = next(p for p in parts if p is not None)
-        dev = some[0].device
-        send_counts = torch.tensor([0 if p is None else p[0].shape[0] for p in parts], dtype=torch.int64, device=dev)
+        if hasattr(self.vol, "route_export"):
+            return self._route_records()
+        keys, tsdf, weight, rgb = self._export_non_owned()
+        dev = keys.device
+        n = keys.shape[0]
+        owner = owner_of(keys[:, self.AXIS].to(torch.int64), world, self.slab_blocks)
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=world)
+        rec = torch.empty((n, self.RECORD), dtype=torch.float32, device=dev)
+        if n:
+            rec[:, :3] = keys.view(torch.float32)
+            rec[:, 3] = 0
+            rec[:, 4:516] = tsdf
+            rec[:, 516:1028] = weight
+            rec[:, 1028:] = rgb.reshape(n, 1536)
+            rec = rec.index_select(0, order)
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
         sc, rc = send_counts.tolist(), recv_counts.tolist()
         self.last_sent, self.last_received = int(sum(sc)), int(sum(rc))
         if self.last_sent == 0 and self.last_received == 0:
             return 0
-
-        def exchange(idx, row_shape, dtype):
-            rows = [p[idx].reshape(p[idx].shape[0], -1) for p in parts if p is not None and p[idx].shape[0] > 0]
-            width = int(np.prod(row_shape))
-            send = torch.cat(rows) if rows else torch.empty((0, width), dtype=dtype, device=dev)
-            recv = torch.empty((sum(rc), width), dtype=dtype, device=dev)
-            dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc,
-                                   group=self.group)
-            return recv.reshape((sum(rc),) + tuple(row_shape))
-
-        keys = exchange(0, (3,), torch.int32)
-        tsdf = exchange(1, (512,), torch.float32)
-        weight = exchange(2, (512,), torch.float32)
-        rgb = exchange(3, (512, 3), torch.float32)
-        # a block can arrive from several ranks: merge one source rank at a time so that
-        # keys are unique inside each merge call
+        recv = torch.empty((sum(rc), self.RECORD), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(recv, rec.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=self.group)
         off = 0
-        for n in rc:
-            if n > 0:
-                self.vol.merge_blocks(keys[off:off + n].contiguous(), tsdf[off:off + n].contiguous(),
-                                      weight[off:off + n].contiguous(), rgb[off:off + n].contiguous())
-            off += n
+        for cnt in rc:
+            if cnt > 0:
+                seg = recv[off:off + cnt]
+                self.vol.merge_blocks(seg[:, :3].contiguous().view(torch.int32), seg[:, 4:516].contiguous(),
+                                      seg[:, 516:1028].contiguous(),
+                                      seg[:, 1028:].contiguous().reshape(cnt, 512, 3))
+            off += cnt
         return self.last_received
+
+
+def _route_records_impl(self):
+    """Device path: the library counts, packs (grouped by destination) and merges wire
+    records itself; torch.distributed only moves them."""
+    import torch
+    import torch.distributed as dist
+    vol, world, rank = self.vol, self.world, self.rank
+    send_counts = vol.route_counts(self.AXIS, self.slab_blocks, world, rank)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+    both = torch.stack([send_counts, recv_counts]).tolist()      # the route's only host sync
+    sc, rc = both[0], both[1]
+    self.last_sent, self.last_received = int(sum(sc)), int(sum(rc))
+    if self.last_sent == 0 and self.last_received == 0:
+        return 0
+    rec = vol.route_export(self.AXIS, self.slab_blocks, world, rank, send_counts, total=self.last_sent)
+    recv = torch.empty((sum(rc), vol.RECORD_WORDS), dtype=torch.float32, device=rec.device)
+    dist.all_to_all_single(recv, rec, output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+    off = 0
+    for cnt in rc:          # one merge per source rank: keys are unique per source
+        if cnt > 0:
+            vol.merge_records(recv[off:off + cnt])
+        off += cnt
+    return self.last_received
+
+
+BlockRouter._route_records = _route_records_impl
 
 
 def allreduce_normal_equations(acc27, sum_d2, count, device=None, group=None):

@@ -427,6 +427,54 @@ class TSDFVolume:
                                                         _ptr(w), _ptr(rgb), n, _ptr(out_b), _stream()))
         return keys[:n], tsdf[:n], w[:n], rgb[:n]
 
+    def export_blocks_outside(self, axis, lo, hi):
+        """Blocks with key[axis] NOT in [lo, hi) — what this rank does not own — in one call.
+        The buffers are sized from the previous call (one retry if the set grew)."""
+        torch = _torch()
+        dev = self.ctx.device
+        cap = max(int(getattr(self, "_outside_cap", 0)), 1024)
+        out_b = torch.zeros(1, dtype=torch.int64, device=dev)
+        while True:
+            keys = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+            tsdf = torch.empty((cap, 512), dtype=torch.float32, device=dev)
+            w = torch.empty((cap, 512), dtype=torch.float32, device=dev)
+            rgb = torch.empty((cap, 512, 3), dtype=torch.float32, device=dev)
+            rc = self.lib.t3d_tsdf_export_blocks_outside(self.handle, int(axis), int(lo), int(hi), _ptr(keys), _ptr(tsdf),
+                                                         _ptr(w), _ptr(rgb), cap, _ptr(out_b), _stream())
+            n = int(out_b.item())
+            if rc == _lib.T3D_E_CAPACITY and n > cap:
+                cap = int(n * 1.25) + 64
+                continue
+            check(rc)
+            self._outside_cap = max(cap, int(n * 1.25) + 64)
+            return keys[:n], tsdf[:n], w[:n], rgb[:n]
+
+    RECORD_WORDS = 4 + 5 * 512
+
+    def route_counts(self, axis, slab_blocks, world, rank):
+        """int32[world] (device): blocks owned by every other rank."""
+        torch = _torch()
+        counts = torch.zeros(world, dtype=torch.int32, device=self.ctx.device)
+        check(self.lib.t3d_tsdf_route_counts(self.handle, int(axis), int(slab_blocks), int(world), int(rank),
+                                             _ptr(counts), _stream()))
+        return counts
+
+    def route_export(self, axis, slab_blocks, world, rank, counts, total=None):
+        """Non-owned blocks as wire records [n, 2564] f32, grouped by destination rank.
+        total: sum(counts) if the caller already has it on the host (saves a sync)."""
+        torch = _torch()
+        base = (torch.cumsum(counts, 0, dtype=torch.int32) - counts).contiguous()
+        n = int(counts.sum().item()) if total is None else int(total)
+        rec = torch.empty((max(n, 1), self.RECORD_WORDS), dtype=torch.float32, device=self.ctx.device)
+        fill = torch.zeros_like(counts)
+        check(self.lib.t3d_tsdf_route_export(self.handle, int(axis), int(slab_blocks), int(world), int(rank),
+                                             _ptr(base), _ptr(fill), _ptr(rec), _stream()))
+        return rec[:n]
+
+    def merge_records(self, records):
+        assert records.is_contiguous()
+        check(self.lib.t3d_tsdf_merge_records(self.handle, _ptr(records), records.shape[0], _stream()))
+
     def merge_blocks(self, keys, tsdf, weight, rgb):
         check(self.lib.t3d_tsdf_merge_blocks(self.handle, _ptr(keys), _ptr(tsdf), _ptr(weight), _ptr(rgb),
                                              keys.shape[0], _stream()))
