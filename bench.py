@@ -141,7 +141,7 @@ def run_reference(args):
         ov = step()
     dt = time.perf_counter() - t0
     fps = args.steps * len(frames) / dt
-    sample = (f"frames 0..{len(frames) - 1} of the 300 cfg2 frames per step (new volume + touch + integrate), "
+    sample = (f"frames 0..{len(frames) - 1} of the workload's frames per step (new volume + touch + integrate), "
               f"oracle/t3d_oracle.c, {cores} OpenMP threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
@@ -179,12 +179,15 @@ def make_host_frames(n, first=0):
     return out
 
 
+WORKLOAD_NAME = ("BASELINE configs[1]: TSDF integration, 300 synthetic 1080x1920 frames, 1 cm voxels, "
+                 "8^3 blocks, trunc 4 cm, depth_max 5 m, known poses")
+
+
 def workload_config(frames, world):
-    return {"workload": "BASELINE configs[1]: TSDF integration, 300 synthetic 1080x1920 frames, 1 cm voxels, "
-                        "8^3 blocks, trunc 4 cm, depth_max 5 m, known poses",
+    return {"workload": WORKLOAD_NAME,
             "frames_per_step_per_gpu": frames, "H": H, "W": W, "voxel_size": VOXEL, "sdf_trunc": TRUNC,
             "depth_max": DEPTH_MAX, "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU",
-            "l2": "inputs (4.35 GB of frames per step) exceed the 126 MB L2; no explicit flush"}
+            "l2": f"inputs ({frames * H * W * 7 / 1e9:.2f} GB of frames per step) exceed the 126 MB L2; no explicit flush"}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -281,7 +284,7 @@ def run_ours(args):
     k5_ms_per_launch = prof["integrate_ms"] / max(prof["calls"], 1)
     k4_ms_per_launch = prof["touch_ms"] / max(prof["calls"], 1)
     achieved = (alg_bytes_step / calls_per_step) / (k5_ms_per_launch * 1e-3) / 1e9
-    traffic, tinfo = load_traffic()
+    traffic, tinfo = load_traffic() if args.workload == "cfg2" else (None, None)
     traffic_src = None if tinfo is None else tinfo.get("source")
     roofline = {
         "kernel": "integrate_kernel (K5)", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -408,7 +411,7 @@ def cpu_baseline(args, depth_all, bgr_all, poses):
         ov.integrate(d, c, KINTR, T, 1.0, DEPTH_MAX)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"frames 0..{n - 1} of the 300 cfg2 frames, one pass (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s wall",
+            "sample": f"frames 0..{n - 1} of the workload's {args.frames} frames, one pass (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s wall",
             "voxel_updates": ov.counters()["voxel_updates"]}
 
 
@@ -525,8 +528,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     ap.add_argument("--serial-batches", action="store_true", help="(tuning) no K4/K5 overlap")
-    ap.add_argument("--workload", choices=["cfg2", "cfg3"], default="cfg2",
-                    help="cfg2 = the driver's headline (TSDF integration, known poses); cfg3 = ICP + TSDF loop")
+    ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg5"], default="cfg2",
+                    help="cfg2 = the driver's headline (TSDF integration, known poses); cfg3 = ICP + TSDF loop; "
+                         "cfg5 = cfg2's path at 2160x3840, 5 mm voxels, trunc 2 cm (BASELINE configs[4])")
     ap.add_argument("--icp-subsample", type=int, default=4)
     ap.add_argument("--icp-max-corr", type=float, default=0.05)
     ap.add_argument("--cpu-frames3", type=int, default=6)
@@ -534,6 +538,18 @@ def main():
     if args.workload == "cfg3":
         run_cfg3(args)
         return
+    if args.workload == "cfg5":
+        global H, W, KINTR, VOXEL, TRUNC, METRIC, WORKLOAD_NAME
+        H, W, KINTR, VOXEL, TRUNC = 3840, 2160, (3438.0, 3438.0, 1080.0, 1920.0), 0.005, 0.02
+        METRIC = "RGB-D frames fused/sec @2160x3840 (TSDF integration, cfg5)"
+        WORKLOAD_NAME = ("BASELINE configs[4]: spatially sharded TSDF of synthetic 2160x3840 frames, 5 mm voxels, "
+                         "8^3 blocks, trunc 2 cm, depth_max 5 m, known poses (frames per GPU as given)")
+        if args.frames == 300:
+            args.frames = 64
+        if args.block_capacity == 600_000:
+            args.block_capacity = 1_500_000
+        if args.cpu_frames == 300:
+            args.cpu_frames = 8
     if args.impl == "reference":
         run_reference(args)
     else:

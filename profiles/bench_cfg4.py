@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""BASELINE config 4: voxel_down_sample (+ estimate_normals on the result) sweep on
+10M..500M fused points (tunnel T1 clouds, f32 xyz + u8 rgb), with size-independent
+exactness properties checked at every size:
+  * sum of per-voxel counts == N                      (no point lost / double counted)
+  * idempotence: down-sampling the voxel centres of the result with the same grid origin
+    gives back exactly the same voxel index set       (hash dedup bit-exactness)
+  * the first 4M points agree with the CPU oracle bit-for-bit on the index set and counts.
+    python profiles/bench_cfg4.py [--sizes 10,50,100,250,500] > gpurun_out/cfg4_rN.jsonl
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+H, W = 1920, 1080
+K4 = (1719.0, 1719.0, 540.0, 960.0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="10,50,100,250,500", help="millions of points")
+    ap.add_argument("--voxels", default="0.005,0.01,0.02")
+    ap.add_argument("--normals-max", type=int, default=20_000_000)
+    args = ap.parse_args()
+    import torch
+    from oracle import capi
+    from textureless_3d_reconstruction_b200.runtime import get_context
+    ctx = get_context(0)
+    dev = ctx.device
+    peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]) if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+    sizes = [int(float(s) * 1e6) for s in args.sizes.split(",")]
+    nmax = max(sizes)
+    pts = torch.empty((nmax, 3), dtype=torch.float32, device=dev)
+    rgb = torch.empty((nmax, 3), dtype=torch.uint8, device=dev)
+    # fused cloud: back-project consecutive T1 frames (depth < 5 m) until nmax points exist
+    B = 16
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    bgr = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    o_xyz = torch.empty((B * H * W, 3), dtype=torch.float32, device=dev)
+    o_rgb = torch.empty((B * H * W, 3), dtype=torch.uint8, device=dev)
+    filled, f0 = 0, 0
+    while filled < nmax:
+        poses = []
+        for i in range(B):
+            _, _, T = ctx.synth_frame(0, f0 + i, H, W, *K4, seed=1234, noise_sigma=0.002, depth=depth[i], bgr=bgr[i])
+            poses.append((T[:, :3].copy(), T[:, 3:4].copy()))
+        fr = ctx.make_backproject_frames([depth[i] for i in range(B)], [bgr[i] for i in range(B)], poses)
+        _, _, offs = ctx.backproject_batch(fr, B, H, W, fx=K4[0], fy=K4[1], cx=K4[2], cy=K4[3], max_depth=5.0,
+                                           out_xyz=o_xyz, out_rgb=o_rgb)
+        n = min(int(offs[-1].item()), nmax - filled)
+        pts[filled:filled + n] = o_xyz[:n]
+        rgb[filled:filled + n] = o_rgb[:n]
+        filled += n
+        f0 += B
+    del depth, bgr, o_xyz, o_rgb
+    torch.cuda.empty_cache()
+    print(json.dumps({"info": f"fused cloud of {nmax} points from {f0} T1 frames"}), flush=True)
+
+    for N in sizes:
+        p, c = pts[:N], rgb[:N]
+        for v in [float(x) for x in args.voxels.split(",")]:
+            torch.cuda.synchronize()
+            r = ctx.voxel_downsample(p, c, v, sorted_output=False, want_idx=True)        # warm (allocations)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = ctx.voxel_downsample(p, c, v, sorted_output=False, want_idx=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            M = r["m"]
+            count_ok = int(r["count"].to(torch.int64).sum().item()) == N
+            # idempotence on the voxel centres
+            centres = (r["idx"].to(torch.float64) + 0.5) * v + torch.from_numpy(r["min_bound"]).to(dev)
+            r2 = ctx.voxel_downsample(centres.contiguous(), None, v, min_bound=r["min_bound"], sorted_output=True,
+                                      want_idx=True)
+            rs = ctx.voxel_downsample(p, c, v, sorted_output=True, want_idx=True)
+            idem = r2["m"] == M and bool(torch.equal(r2["idx"], rs["idx"]))
+            line = {"kernel": "K2 voxel_downsample", "points": N, "voxel": v, "voxels_out": M, "ms": ms,
+                    "points_per_s": N / (ms * 1e-3), "algorithmic_bytes": 15 * N + 27 * M,
+                    "achieved_GBs": (15 * N + 27 * M) / (ms * 1e-3) / 1e9, "peak_GBs": peak,
+                    "frac": (15 * N + 27 * M) / (ms * 1e-3) / 1e9 / peak, "sum_count_equals_N": count_ok,
+                    "idempotent_index_set": idem}
+            if N == sizes[0]:
+                ns = min(N, 4_000_000)
+                t0 = time.perf_counter()
+                o = capi.voxel_downsample(p[:ns].cpu().numpy().astype(np.float64), c[:ns].cpu().numpy(), v)
+                cpu_s = time.perf_counter() - t0
+                g = ctx.voxel_downsample(p[:ns].contiguous(), c[:ns].contiguous(), v, sorted_output=True, want_idx=True)
+                oo = np.lexsort(o["idx"].T[::-1])
+                line["oracle_4M_bit_exact"] = bool(np.array_equal(g["idx"].cpu().numpy(), o["idx"][oo]) and
+                                                   np.array_equal(g["count"].cpu().numpy().astype(np.uint32), o["count"][oo]))
+                line["cpu_baseline"] = {"points_per_s": ns / cpu_s, "cores": 1, "kind": "port",
+                                        "sample": f"first {ns} points, serial hash (Open3D's VoxelDownSample is serial)"}
+            print(json.dumps(line), flush=True)
+            del r, r2, rs, centres
+            torch.cuda.empty_cache()
+        # estimate_normals knn=30 on the v=0.01 result (bounded)
+        ds = ctx.voxel_downsample(p, c, 0.01, sorted_output=True, want_idx=False)
+        q = ds["points"].to(torch.float32)[: args.normals_max].contiguous()
+        del ds
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nrm = ctx.estimate_normals(q, 30)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        unit = bool(((nrm.norm(dim=1) - 1).abs() < 1e-4).all().item())
+        print(json.dumps({"kernel": "K7 estimate_normals knn=30 on the 1 cm downsample", "input_points": N,
+                          "points": int(q.shape[0]), "ms": ms, "points_per_s": q.shape[0] / (ms * 1e-3),
+                          "unit_length": unit}), flush=True)
+        del q, nrm
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
