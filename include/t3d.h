@@ -241,7 +241,9 @@ int t3d_tsdf_export_blocks_outside(t3d_tsdf* v, int axis, int32_t lo, int32_t hi
                                    float* rgb, int64_t capacity, int64_t* out_b,
                                    t3d_stream stream);
 /* Merge partial blocks into the volume (multi-GPU owner reduce):
- * w' = w_a + w_b, tsdf' = (w_a*tsdf_a + w_b*tsdf_b)/w', same for rgb. */
+ * w' = w_a + w_b, tsdf' = (w_a*tsdf_a + w_b*tsdf_b)/w', same for rgb; a voxel with
+ * w_a == 0 (or w_b == 0) takes the other side's values unchanged, so restoring a dump
+ * into an empty volume is bit-exact. */
 int t3d_tsdf_merge_blocks(t3d_tsdf* v, const int32_t* keys, const float* tsdf,
                           const float* weight, const float* rgb, int64_t b,
                           t3d_stream stream);
@@ -339,6 +341,39 @@ int t3d_nearest_neighbor(t3d_ctx* ctx, const float* query, int64_t n_q,
 int t3d_write_ply_h(const char* path, const void* xyz_h, int xyz_is_f64,
                     const uint8_t* rgb_h, const void* nrm_h, int64_t n,
                     int layout);
+
+/* ------------------------------------------------------------------------- */
+/* Formats either side of the path.                              */
+/* ------------------------------------------------------------------------- */
+/* 16-bit millimetre depth -> float32: out = (float)raw / divisor — the reader's
+ * `raw.astype(np.float32) / 1000.0` (d2r:85-90) on the GPU (a depth PNG then crosses
+ * PCIe at 2 B/pixel). */
+int t3d_depth_u16_to_f32(t3d_ctx* ctx, const uint16_t* raw, int64_t n, float divisor,
+                         float* out, t3d_stream stream);
+/* float32 depth -> 16-bit: out = (depth * factor).astype(np.uint16), the writer's
+ * `(depth * 1000).astype(np.uint16)` (dp:919-921) including its wrap-around for
+ * out-of-range / non-finite values (x86-64 NumPy conversion). */
+int t3d_depth_f32_to_u16(t3d_ctx* ctx, const float* depth, int64_t n, float factor,
+                         uint16_t* out, t3d_stream stream);
+/* cv2.resize(depth, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for float32
+ * single-channel images (d2r:465-467).  Pinned against OpenCV 4.13 outputs
+ * (tests/golden/formats.npz); tolerance 1e-6 relative (SIMD contraction differs). */
+int t3d_resize_bilinear_f32(t3d_ctx* ctx, const float* src, int src_h, int src_w,
+                            float* dst, int dst_h, int dst_w, t3d_stream stream);
+/* Depth-scale estimation (d2r:297-326 with gate=1; der:652-697 with gate=0 and
+ * min_input_points=5): median over sparse points of Z_i / depth[int(v_i), int(u_i)].
+ * depth: device H*W f32.  pts3d_h (n*3) / pts2d_h (n*2): host f64.  Returns 1.0 with
+ * fewer than 3 accepted samples.  Synchronous. */
+int t3d_estimate_scale(t3d_ctx* ctx, const float* depth, int H, int W,
+                       const double* pts3d_h, const double* pts2d_h, int64_t n,
+                       int gate, int min_input_points, double* out_scale_h,
+                       int64_t* out_samples_h, t3d_stream stream);
+/* PointCloud2 records (dp:744-758): out[i] = {x, y, z, rgb} with rgb = the bytes
+ * (b, g, r, 0) reinterpreted as float32; colours are f32 in [0,1] (r,g,b =
+ * (c*255).astype(uint8), colors_are_f32 != 0) or u8 RGB.  out_records: n*4 f32. */
+int t3d_pack_pointcloud2(t3d_ctx* ctx, const float* xyz, const void* colors,
+                         int colors_are_f32, int64_t n, float* out_records,
+                         t3d_stream stream);
 
 /* ------------------------------------------------------------------------- */
 /* Synthetic scenes: device-side generators used by bench.py and */

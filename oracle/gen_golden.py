@@ -177,7 +177,71 @@ def main():
                              "depth_{stem}.npy", "depth_{stem}.png"],
     )
     (OUT / "intrinsics_config.json").write_text(json.dumps(golden, indent=1))
+    gen_formats(d2r, der)
     print("wrote", sorted(p.name for p in OUT.iterdir()))
+
+
+def gen_formats(d2r, der):
+    """tests/golden/formats.npz — SURVEY 8f rows: depth file formats (dp:905-921 writer, d2r:80-97
+    reader, run through cv2 / NumPy exactly as the reference does), depth->RGB resize (cv2.resize
+    INTER_LINEAR, d2r:465-467), depth-scale estimation (the reference's own two functions), and the
+    PointCloud2 colour packing (statements of dp:750-756 executed verbatim; the enclosing class needs ROS)."""
+    import cv2
+    rng = np.random.default_rng(77)
+    out = {}
+    # 16-bit millimetre depth: writer then reader, through real PNG files
+    depth = rng.uniform(0.0, 70.0, size=(41, 57)).astype(np.float32)
+    flat = depth.reshape(-1)
+    for k, v in enumerate([0.0, 65.535, 65.5351, 65.536, 65.5365, 131.072, 1e-4, 0.0005, 0.001, 0.0019999, np.nan,
+                           np.inf, -np.inf, -0.001, -1.0, -65.536, 3e9, -3e9, 2147483.5, 2147483.9]):
+        flat[k * 7] = np.float32(v)
+    with np.errstate(invalid="ignore"):
+        depth_mm = (depth * 1000).astype(np.uint16)                                    # dp:920
+    with tempfile.TemporaryDirectory() as td:
+        f = Path(td) / "a_depth.png"
+        cv2.imwrite(str(f), depth_mm)                                                    # dp:921
+        back = d2r.DepthImageLoader.load_depth(f)                                        # d2r:85-90
+        np.save(Path(td) / "a_depth.npy", depth)                                         # dp:908
+        back_npy = d2r.DepthImageLoader.load_depth(Path(td) / "a_depth.npy")
+    out.update(depth=depth, depth_mm=depth_mm, depth_back=back, depth_back_npy=back_npy)
+    # cv2.resize INTER_LINEAR (d2r:465-467): depth -> RGB size
+    src = rng.uniform(0.2, 9.0, size=(37, 53)).astype(np.float32)
+    src[5, 7] = 0.0
+    rs = []
+    for i, (dh, dw) in enumerate([(74, 106), (100, 91), (37, 53), (18, 26), (19, 27), (120, 160), (1, 1), (3, 200)]):
+        out[f"resize_{i}"] = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        rs.append([dh, dw])
+    src2 = rng.uniform(0.2, 9.0, size=(120, 160)).astype(np.float32)
+    out["resize_src2_half"] = cv2.resize(src2, (80, 60), interpolation=cv2.INTER_LINEAR)  # exact 2x: cv2's area fast path
+    out.update(resize_src=src, resize_shapes=np.array(rs), resize_src2=src2)
+    # depth-scale estimation: the reference's two functions
+    dm = rng.uniform(0.0, 4.0, size=(48, 64)).astype(np.float32)
+    dm[rng.uniform(size=dm.shape) < 0.1] = 0.0
+    cfg = d2r.ReconstructionConfig()
+    dense = d2r.DenseReconstructor(cfg)
+    sc = []
+    for i, n in enumerate([0, 2, 3, 4, 5, 40, 41, 300]):
+        p3 = rng.uniform(-2.0, 6.0, size=(n, 3))
+        p2 = np.column_stack([rng.uniform(-6.0, 70.0, n), rng.uniform(-6.0, 54.0, n)])
+        if n >= 40:
+            p3[0, 2] = 1e5                                                               # ratio > 1000: gated in d2r only
+            p3[1, 2] = 1e-6
+            p2[2] = [-0.5, -0.7]                                                         # int() truncates toward 0 -> pixel (0,0)
+        with redirect_stdout(io.StringIO()):
+            s_d2r = dense.estimate_scale(p3, p2, dm)
+            s_der = der.DepthScaleEstimator.estimate_scale(p3, p2, dm, cfg.K)
+        out[f"scale_{i}_p3"], out[f"scale_{i}_p2"] = p3, p2
+        sc.append([float(s_d2r), float(s_der)])
+    out.update(scale_depth=dm, scale_expected=np.array(sc))
+    # PointCloud2 colour packing, dp:750-756
+    pts = rng.uniform(-3, 3, size=(300, 3)).astype(np.float32)
+    cols = (rng.integers(0, 256, size=(300, 3)).astype(np.float32) / 255.0)[:, ::-1].copy()   # dp:417-420 output format
+    rgb_packed = np.zeros(len(pts), dtype=np.float32)
+    for i in range(len(pts)):
+        r, g, b = (cols[i] * 255).astype(np.uint8)
+        rgb_packed[i] = np.frombuffer(np.array([b, g, r, 0], dtype=np.uint8).tobytes(), dtype=np.float32)[0]
+    out.update(pc2_points=pts, pc2_colors=cols, pc2_cloud=np.column_stack([pts, rgb_packed]).view(np.uint32))
+    np.savez_compressed(OUT / "formats.npz", **out)
 
 
 if __name__ == "__main__":

@@ -279,3 +279,27 @@ def test_route_records_round_trip(ctx):
     for x, y in zip(ga, gb):
         assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
                               y.view(np.uint32) if y.dtype == np.float32 else y)
+
+
+def test_checkpoint_resume_is_bit_exact(ctx, tmp_path):
+    """save() after k frames + load() + the remaining frames == uninterrupted fusion, bit for bit."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(6, H, W)
+    full = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    part = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    for i, (d, c, T) in enumerate(fr):
+        full.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+        if i < 3:
+            part.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    part.save(tmp_path / "vol.npz")
+    res = TSDFVolume.load(tmp_path / "vol.npz", block_capacity=60000, ctx=ctx)
+    assert res.num_blocks == part.num_blocks
+    for d, c, T in fr[3:]:
+        res.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    a = by_key(*[x.cpu().numpy() for x in full.export_blocks()])
+    b = by_key(*[x.cpu().numpy() for x in res.export_blocks()])
+    for x, y in zip(a, b):
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
+                              y.view(np.uint32) if y.dtype == np.float32 else y)

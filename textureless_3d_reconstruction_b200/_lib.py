@@ -98,6 +98,11 @@ _SIGS = {
     "t3d_icp_point_to_plane": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _I, _D, _D, C.POINTER(IcpResult), _VP]),
     "t3d_icp_linearize": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _VP, _VP, _VP]),
     "t3d_nearest_neighbor": (_I, [_VP, _VP, _I64, _VP, _I64, _D, _VP, _VP, _VP]),
+    "t3d_depth_u16_to_f32": (_I, [_VP, _VP, _I64, _F, _VP, _VP]),
+    "t3d_depth_f32_to_u16": (_I, [_VP, _VP, _I64, _F, _VP, _VP]),
+    "t3d_resize_bilinear_f32": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
+    "t3d_estimate_scale": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I64, _I, _I, _VP, _VP, _VP]),
+    "t3d_pack_pointcloud2": (_I, [_VP, _VP, _VP, _I, _I64, _VP, _VP]),
     "t3d_write_ply_h": (_I, [C.c_char_p, _VP, _I, _VP, _VP, _I64, _I]),
     "t3d_synth_frame": (_I, [_VP, _I, _I, _I, _I, _D, _D, _D, _D, C.c_uint64, _F, _VP, _VP, _VP, _VP]),
 }

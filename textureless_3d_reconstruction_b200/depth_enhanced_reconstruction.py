@@ -91,6 +91,24 @@ class DensePointCloudGenerator:
         return points, colors
 
 
+class DepthScaleEstimator:
+    """der:652-697 — median of Z/d over sparse points (no sanity gate in this copy; at least 5
+    sparse points and 3 accepted samples, else 1.0)."""
+
+    @staticmethod
+    def estimate_scale(sparse_points: np.ndarray, sparse_pts2d: np.ndarray, depth_map, K: np.ndarray = None) -> float:
+        import torch
+        ctx = get_context()
+        d = depth_map if isinstance(depth_map, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(depth_map, np.float32)).to(ctx.device)
+        scale, n = ctx.estimate_scale(d.contiguous(), sparse_points, sparse_pts2d, gate=False, min_input_points=5)
+        if n < 3:
+            return 1.0
+        scale = np.float64(scale)
+        print(f"  Depth scale: {scale:.4f} (from {n} points)")
+        return scale
+
+
 class DepthEnhancedReconstruction:
     """der:896-1311 with the pose step = frame-to-model ICP and the merge = TSDF fusion."""
 

@@ -92,5 +92,36 @@ class PointCloudGenerator:
             cols = np.floor(cols * 255.0 + 0.5).astype(np.uint8)     # Open3D ColorToUint8 (R9)
         write_ply(filepath, points, cols, layout=_lib.PLY_O3D_BINARY)
 
+    def pointcloud2_records(self, points, colors):
+        """The PointCloud2 payload of ROS2DepthPublisher.publish_pointcloud (dp:726-764): one
+        16-byte record x, y, z, rgb per point with rgb = bytes (b, g, r, 0) viewed as float32 —
+        packed by one kernel instead of the reference's per-point Python loop (dp:750-756).
+        points (N,3) f32 / colors (N,3) f32 in [0,1]; host arrays or CUDA tensors.  Returns
+        an (N,4) f32 array of the same kind."""
+        import torch
+        host = not isinstance(points, torch.Tensor)
+        dev = self.ctx.device
+        p = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev) if host else points.contiguous()
+        c = torch.from_numpy(np.ascontiguousarray(colors, np.float32)).to(dev) if host else colors.contiguous()
+        rec = self.ctx.pack_pointcloud2(p, c)
+        return rec.cpu().numpy() if host else rec
+
     def save_pcd(self, filepath: str, points: np.ndarray, colors: Optional[np.ndarray] = None):
         self.save_ply(filepath.replace(".ply", ".pcd"), points, colors)   # dp:442-450 (same quirk)
+
+
+def save_depth_files(depth, identifier: str, depth_dir, save_raw_depth: bool = True, ctx=None):
+    """The depth outputs of DepthProcessor._save_depth (dp:905-921) that depth_to_reconstruction reads
+    back: `{id}_depth.npy` (float32 metres) and `{id}_depth.png` (16-bit millimetres,
+    `(depth*1000).astype(uint16)` computed on the GPU).  depth: (H,W) f32 host array or CUDA tensor."""
+    import cv2
+    import torch
+    from pathlib import Path
+    ctx = ctx or get_context()
+    d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth, np.float32)).to(ctx.device)
+    depth_dir = Path(depth_dir)
+    depth_dir.mkdir(parents=True, exist_ok=True)
+    if save_raw_depth:
+        np.save(depth_dir / f"{identifier}_depth.npy", d.cpu().numpy())
+    mm = ctx.depth_f32_to_u16(d.contiguous()).cpu().numpy()
+    cv2.imwrite(str(depth_dir / f"{identifier}_depth.png"), mm)

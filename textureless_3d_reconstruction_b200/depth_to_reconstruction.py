@@ -61,6 +61,25 @@ class DepthImageLoader:
         return None
 
     @staticmethod
+    def load_depth_device(filepath: Path, ctx=None):
+        """Same files, decoded on the GPU: a 16-bit millimetre PNG is uploaded raw (2 B/pixel)
+        and divided by 1000 there (t3d_depth_u16_to_f32) — bit-identical to load_depth().
+        Returns an (H,W) f32 CUDA tensor or None."""
+        import torch
+        filepath = Path(filepath)
+        ctx = ctx or get_context()
+        if filepath.suffix == ".png":
+            import cv2
+            raw = cv2.imread(str(filepath), cv2.IMREAD_ANYDEPTH)
+            if raw is None:
+                return None
+            if raw.dtype == np.uint16:
+                return ctx.depth_u16_to_f32(torch.from_numpy(raw.view(np.int16)).to(ctx.device), 1000.0)
+            return torch.from_numpy(raw.astype(np.float32) / 1000.0).to(ctx.device)
+        d = DepthImageLoader.load_depth(filepath)
+        return None if d is None else torch.from_numpy(np.ascontiguousarray(d)).to(ctx.device)
+
+    @staticmethod
     def find_matching_depth(rgb_name: str, depth_folder: Path) -> Optional[Path]:
         stem = Path(rgb_name).stem
         for cand in (f"{stem}_depth.npy", f"{stem}_depth.png", f"{stem}.npy", f"{stem}.png",
@@ -93,20 +112,20 @@ class DenseReconstructor:
         return self._ctx
 
     def estimate_scale(self, sparse_points, sparse_pts2d, depth_map) -> float:
-        """d2r:297-326 (tiny host-side scalar; kept for API completeness)."""
-        h, w = depth_map.shape
-        ratios = []
-        for p3, p2 in zip(sparse_points, sparse_pts2d):
-            x, y = int(p2[0]), int(p2[1])
-            if 0 <= x < w and 0 <= y < h:
-                dn, ds = depth_map[y, x], p3[2]
-                if dn > 0 and ds > 0 and 0.001 < ds / dn < 1000:
-                    ratios.append(ds / dn)
-        if len(ratios) < 3:
+        """d2r:297-326 — median of Z/d over the sparse points with the 0.001 < s < 1000 gate
+        (t3d_estimate_scale; depth_map may be a host array or an (H,W) f32 CUDA tensor)."""
+        import torch
+        if min(len(sparse_points), len(sparse_pts2d)) < 3:     # cannot reach 3 samples: no device work
             print("Warning: Too few scale samples, using default scale=1.0")
             return 1.0
-        scale = np.median(ratios)
-        print(f"Estimated depth scale: {scale:.6f} (from {len(ratios)} samples)")
+        d = depth_map if isinstance(depth_map, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(depth_map, np.float32)).to(self.ctx.device)
+        scale, n = self.ctx.estimate_scale(d.contiguous(), sparse_points, sparse_pts2d, gate=True)
+        if n < 3:
+            print("Warning: Too few scale samples, using default scale=1.0")
+            return 1.0
+        scale = np.float64(scale)          # np.median returns np.float64: keeps `depth * scale` in f64 (d2r:356)
+        print(f"Estimated depth scale: {scale:.6f} (from {n} samples)")
         return scale
 
     def depth_to_pointcloud_device(self, depth, color, pose=None, scale=1.0, subsample=1):
@@ -197,8 +216,11 @@ class DepthToReconstructionPipeline:
             depth = DepthImageLoader.load_depth(df)
             if depth is None:
                 continue
-            if depth.shape[:2] != img.shape[:2]:
-                depth = cv2.resize(depth, (img.shape[1], img.shape[0]), interpolation=cv2.INTER_LINEAR)
+            if depth.shape[:2] != img.shape[:2]:          # d2r:465-467, cv2.INTER_LINEAR semantics on the GPU
+                import torch
+                ctx = self.dense.ctx
+                depth = ctx.resize_bilinear(torch.from_numpy(np.ascontiguousarray(depth, np.float32)).to(ctx.device),
+                                            img.shape[0], img.shape[1]).cpu().numpy()
             self.images.append(img)
             self.depths.append(depth)
             self.image_names.append(rf.name)

@@ -264,6 +264,55 @@ class Context:
                                             float(radius), _ptr(idx), _ptr(d2), _stream()))
         return idx[: query.shape[0]], d2[: query.shape[0]]
 
+    # ------------------------------------------------------------------ formats
+    def depth_u16_to_f32(self, raw, divisor=1000.0):
+        """raw: (H,W) uint16|int16-typed CUDA tensor of millimetres -> f32 metres (d2r:85-90)."""
+        torch = _torch()
+        assert raw.is_cuda and raw.is_contiguous() and raw.element_size() == 2
+        out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+        check(self.lib.t3d_depth_u16_to_f32(self.handle, _ptr(raw), raw.numel(), float(divisor), _ptr(out), _stream()))
+        return out
+
+    def depth_f32_to_u16(self, depth, factor=1000.0):
+        """(depth * 1000).astype(np.uint16) on the GPU (dp:919-921); returns a uint16 tensor."""
+        torch = _torch()
+        assert depth.is_cuda and depth.is_contiguous() and depth.dtype == torch.float32
+        out = torch.empty(depth.shape, dtype=torch.uint16, device=depth.device)
+        check(self.lib.t3d_depth_f32_to_u16(self.handle, _ptr(depth), depth.numel(), float(factor), _ptr(out), _stream()))
+        return out
+
+    def resize_bilinear(self, src, dst_h, dst_w):
+        """cv2.resize(src, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for (H,W) f32 (d2r:465-467)."""
+        torch = _torch()
+        assert src.is_cuda and src.is_contiguous() and src.dtype == torch.float32 and src.dim() == 2
+        out = torch.empty((int(dst_h), int(dst_w)), dtype=torch.float32, device=src.device)
+        check(self.lib.t3d_resize_bilinear_f32(self.handle, _ptr(src), src.shape[0], src.shape[1], _ptr(out),
+                                               int(dst_h), int(dst_w), _stream()))
+        return out
+
+    def estimate_scale(self, depth, sparse_points, sparse_pts2d, gate=True, min_input_points=0):
+        """Median of Z/d over sparse points (d2r:297-326 gate=True; der:652-697 gate=False,
+        min_input_points=5).  depth: (H,W) f32 CUDA tensor.  Returns (scale, n_samples)."""
+        p3 = np.ascontiguousarray(sparse_points, np.float64).reshape(-1, 3)
+        p2 = np.ascontiguousarray(sparse_pts2d, np.float64).reshape(-1, 2)
+        n = min(len(p3), len(p2))
+        s = C.c_double(1.0)
+        k = C.c_int64(0)
+        check(self.lib.t3d_estimate_scale(self.handle, _ptr(depth), depth.shape[0], depth.shape[1], _np_ptr(p3),
+                                          _np_ptr(p2), n, int(bool(gate)), int(min_input_points), C.byref(s),
+                                          C.byref(k), _stream()))
+        return float(s.value), int(k.value)
+
+    def pack_pointcloud2(self, xyz, colors):
+        """PointCloud2 records [N,4] f32 = x, y, z, rgb-as-float-bits (dp:744-758).
+        colors: f32 in [0,1] (PointCloudGenerator.generate output) or u8 RGB."""
+        torch = _torch()
+        assert xyz.is_contiguous() and colors.is_contiguous() and xyz.dtype == torch.float32
+        out = torch.empty((max(xyz.shape[0], 1), 4), dtype=torch.float32, device=xyz.device)
+        check(self.lib.t3d_pack_pointcloud2(self.handle, _ptr(xyz), _ptr(colors), int(colors.dtype == torch.float32),
+                                            xyz.shape[0], _ptr(out), _stream()))
+        return out[: xyz.shape[0]]
+
     # ------------------------------------------------------------------ synth
     def synth_frame(self, scene, frame_index, H, W, fx, fy, cx, cy, seed=1234, noise_sigma=0.0,
                     depth=None, bgr=None, pose_only=False):
@@ -478,6 +527,26 @@ class TSDFVolume:
     def merge_blocks(self, keys, tsdf, weight, rgb):
         check(self.lib.t3d_tsdf_merge_blocks(self.handle, _ptr(keys), _ptr(tsdf), _ptr(weight), _ptr(rgb),
                                              keys.shape[0], _stream()))
+
+    # ---- checkpoint / resume: the block list is the wire format
+    def save(self, path):
+        """Dump the volume (keys + per-voxel tsdf / weight / rgb of every block) to an .npz."""
+        keys, tsdf, w, rgb = self.export_blocks()
+        np.savez(path, keys=keys.cpu().numpy(), tsdf=tsdf.cpu().numpy(), weight=w.cpu().numpy(),
+                 rgb=rgb.cpu().numpy(), voxel_size=np.float32(self.voxel_size), sdf_trunc=np.float32(self.sdf_trunc))
+
+    @classmethod
+    def load(cls, path, block_capacity=None, ctx=None):
+        """Restore a volume saved by save(); fusion can continue on it (weights are kept)."""
+        torch = _torch()
+        z = np.load(path)
+        n = len(z["keys"])
+        vol = cls(float(z["voxel_size"]), float(z["sdf_trunc"]), int(block_capacity or max(2 * n, 1024)), ctx=ctx)
+        dev = vol.ctx.device
+        if n:
+            vol.merge_blocks(torch.from_numpy(z["keys"]).to(dev), torch.from_numpy(z["tsdf"]).to(dev),
+                             torch.from_numpy(z["weight"]).to(dev), torch.from_numpy(z["rgb"]).to(dev))
+        return vol
 
     def extract_points(self, weight_threshold=3.0, with_normals=True, with_colors=True, capacity=None):
         torch = _torch()
