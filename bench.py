@@ -221,8 +221,12 @@ def run_ours(args):
 
     router = None
     if world > 1:
-        from textureless_3d_reconstruction_b200.distributed import BlockRouter
-        router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
+        from textureless_3d_reconstruction_b200.distributed import BlockRouter, P2PBlockRouter
+        if args.router == "p2p":
+            router = P2PBlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8,
+                                    region_records=args.region_records)
+        else:
+            router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
 
     route_events = []
 
@@ -325,10 +329,20 @@ def run_ours(args):
             "blocks_per_gpu": int(nblocks), "batch_frames": B,
         }
         if router is not None:
-            line["routing"] = {"blocks_sent_rank0": router.last_sent, "blocks_received_rank0": router.last_received,
-                               "bytes_sent_rank0": router.last_sent * 4 * router.RECORD,
-                               "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
-                               "collective": "NCCL all_to_all_single (counts) + all_to_all_single (10 KiB block records)"}
+            if args.router == "p2p":
+                sent, dropped = router.stats()
+                line["routing"] = {"blocks_sent_rank0": int(sum(sent)), "records_dropped_rank0": int(dropped),
+                                   "bytes_sent_rank0": int(sum(sent)) * 4 * vol.RECORD_WORDS,
+                                   "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
+                                   "transport": "export kernel stores 10 KiB block records straight into the owner's "
+                                                "memory over NVLink (CUDA IPC peer mapping); 4-byte NCCL all_reduce as "
+                                                "the export->merge fence; owner merges from its own HBM"}
+                assert dropped == 0, "receive region too small: raise --region-records"
+            else:
+                line["routing"] = {"blocks_sent_rank0": router.last_sent, "blocks_received_rank0": router.last_received,
+                                   "bytes_sent_rank0": router.last_sent * 4 * router.RECORD,
+                                   "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
+                                   "transport": "NCCL all_to_all_single (counts) + all_to_all_single (10 KiB block records)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -528,6 +542,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     ap.add_argument("--serial-batches", action="store_true", help="(tuning) no K4/K5 overlap")
+    ap.add_argument("--router", choices=["p2p", "nccl"], default="p2p",
+                    help="N>1 block routing: peer-memory stores over NVLink (default) or NCCL all_to_all")
+    ap.add_argument("--region-records", type=int, default=16384,
+                    help="p2p router: receive capacity per source rank, in 10 KiB block records")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg5"], default="cfg2",
                     help="cfg2 = the driver's headline (TSDF integration, known poses); cfg3 = ICP + TSDF loop; "
                          "cfg5 = cfg2's path at 2160x3840, 5 mm voxels, trunc 2 cm (BASELINE configs[4])")

@@ -266,6 +266,29 @@ int t3d_tsdf_route_export(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
 int t3d_tsdf_merge_records(t3d_tsdf* v, const float* records, int64_t b,
                            t3d_stream stream);
 
+/* Fused export + transfer over peer memory (NVLink/NVSwitch): every non-owned block is stored
+ * straight into its owner's receive region — peer_regions_h[d] is, in rank d's memory (opened
+ * with t3d_ipc_open), the region reserved for records coming from THIS rank; peer_counts_h[d]
+ * the int32 header slot there for this rank's record count, written by the last CTA.
+ * local_fill: device int32[world + 2] scratch ([world] = CTA ticket, [world+1] = records that
+ * did not fit).  The owners then call t3d_tsdf_merge_records_dev on their own memory after a
+ * barrier.  Asynchronous; no staging copy, no collective on the data path. */
+int t3d_tsdf_route_export_p2p(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
+                              int self_rank, void* const* peer_regions_h,
+                              int32_t* const* peer_counts_h, int64_t region_records,
+                              int32_t* local_fill, t3d_stream stream);
+/* t3d_tsdf_merge_records with the record count read from device memory (<= max_b). */
+int t3d_tsdf_merge_records_dev(t3d_tsdf* v, const float* records, const int32_t* count_dev,
+                               int64_t max_b, t3d_stream stream);
+
+/* Peer-visible device buffers (CUDA IPC).  alloc: cudaMalloc + zero + 64-byte handle to
+ * hand to the other ranks; open/close: map/unmap a peer's buffer; free: release one's own. */
+int t3d_ipc_alloc(t3d_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t* handle_out64);
+int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_ptr);
+int t3d_ipc_close(t3d_ctx* ctx, void* dev_ptr);
+int t3d_ipc_free(t3d_ctx* ctx, void* dev_ptr);
+int t3d_memset_async(void* dev_ptr, int value, size_t bytes, t3d_stream stream);
+
 /* K6: surface points (R6).  xyz/nrm: cap*3 f32; rgb: cap*3 u8 (nullable
  * nrm/rgb).  out_n device int64.  Order: deterministic only as a set. */
 int t3d_tsdf_extract_points(t3d_tsdf* v, float weight_threshold, float* xyz,

@@ -303,3 +303,18 @@ def test_checkpoint_resume_is_bit_exact(ctx, tmp_path):
     for x, y in zip(a, b):
         assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
                               y.view(np.uint32) if y.dtype == np.float32 else y)
+
+
+def test_multi_gpu_routers_agree():
+    """Needs >= 2 GPUs (skipped on the 1-GPU tier): tests/mgpu_route_check.py under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tests" / "mgpu_route_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "p2p==nccl True owned==serial True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -91,6 +91,13 @@ _SIGS = {
     "t3d_tsdf_route_counts": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP]),
     "t3d_tsdf_route_export": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _VP, _VP]),
     "t3d_tsdf_merge_records": (_I, [_VP, _VP, _I64, _VP]),
+    "t3d_tsdf_route_export_p2p": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _I64, _VP, _VP]),
+    "t3d_tsdf_merge_records_dev": (_I, [_VP, _VP, _VP, _I64, _VP]),
+    "t3d_ipc_alloc": (_I, [_VP, C.c_size_t, C.POINTER(_VP), _VP]),
+    "t3d_ipc_open": (_I, [_VP, _VP, C.POINTER(_VP)]),
+    "t3d_ipc_close": (_I, [_VP, _VP]),
+    "t3d_ipc_free": (_I, [_VP, _VP]),
+    "t3d_memset_async": (_I, [_VP, _I, C.c_size_t, _VP]),
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),

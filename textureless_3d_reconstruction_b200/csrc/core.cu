@@ -75,3 +75,54 @@ extern "C" void t3d_destroy(t3d_ctx* ctx) {
 extern "C" int64_t t3d_launch_count(const t3d_ctx* ctx) {
   return ctx ? ctx->launches : 0;
 }
+
+// ---------------------------------------------------------------------------
+// Peer memory (multi-GPU block routing over NVLink/NVSwitch): buffers allocated here can be
+// opened by the other ranks of the box through CUDA IPC handles, so an export kernel can
+// store its records straight into the owner's memory.
+// ---------------------------------------------------------------------------
+extern "C" int t3d_ipc_alloc(t3d_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t* handle_out64) {
+  T3D_REQUIRE(ctx && dev_ptr && handle_out64 && bytes > 0, "t3d_ipc_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  T3D_CUDA(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  T3D_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    t3d_set_error("t3d_ipc_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+    return T3D_E_CUDA;
+  }
+  T3D_CUDA(cudaMemset(p, 0, bytes));
+  memcpy(handle_out64, &h, 64);
+  *dev_ptr = p;
+  return T3D_OK;
+}
+
+extern "C" int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_ptr) {
+  T3D_REQUIRE(ctx && handle64 && dev_ptr, "t3d_ipc_open: bad argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  T3D_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return T3D_OK;
+}
+
+extern "C" int t3d_ipc_close(t3d_ctx* ctx, void* dev_ptr) {
+  T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_close: bad argument");
+  T3D_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return T3D_OK;
+}
+
+extern "C" int t3d_ipc_free(t3d_ctx* ctx, void* dev_ptr) {
+  T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_free: bad argument");
+  T3D_CUDA(cudaFree(dev_ptr));
+  return T3D_OK;
+}
+
+extern "C" int t3d_memset_async(void* dev_ptr, int value, size_t bytes, t3d_stream stream) {
+  T3D_REQUIRE(dev_ptr || bytes == 0, "t3d_memset_async: null pointer");
+  if (bytes) T3D_CUDA(cudaMemsetAsync(dev_ptr, value, bytes, as_stream(stream)));
+  return T3D_OK;
+}

@@ -134,6 +134,95 @@ def _route_records_impl(self):
 BlockRouter._route_records = _route_records_impl
 
 
+class P2PBlockRouter:
+    """Block routing over peer memory (one box, NVLink/NVSwitch): the export kernel stores every
+    non-owned block directly into its owner's receive region (CUDA IPC mapping), a tiny
+    all_reduce orders "all exports done" before "merge", and every rank merges the records
+    that landed in its own memory.  No staging buffer, no data-path collective, no host sync.
+
+    Receive buffer of a rank (two of them, used on alternating steps so that a fast neighbour
+    can never overwrite records that are still being merged):
+        [int32 count_from[world] | pad to 256 B][region 0][region 1] ... [region world-1]
+    region s holds up to `region_records` 10 256-byte records coming from rank s."""
+
+    AXIS = 2
+    HEADER = 256
+
+    def __init__(self, vol, rank, world, slab_frames, frame_advance, block_size, region_records=16384, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.vol, self.rank, self.world, self.group = vol, rank, world, group
+        self.lib, self.ctx = vol.lib, vol.ctx
+        self.slab_blocks = max(1, int(round(slab_frames * frame_advance / block_size)))
+        self.region_records = int(region_records)
+        self.region_bytes = self.region_records * vol.RECORD_WORDS * 4
+        total = self.HEADER + world * self.region_bytes
+        self.local, self.peers = [], []
+        for parity in range(2):
+            ptr = C.c_void_p()
+            handle = (C.c_uint8 * 64)()
+            _lib.check(self.lib.t3d_ipc_alloc(self.ctx.handle, total, C.byref(ptr), handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            bases = []
+            for d in range(world):
+                if d == rank:
+                    bases.append(ptr.value)
+                    continue
+                q = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(handles[d])
+                _lib.check(self.lib.t3d_ipc_open(self.ctx.handle, hb, C.byref(q)))
+                bases.append(q.value)
+            self.local.append(ptr.value)
+            self.peers.append(bases)
+        self.fill = torch.zeros(world + 2, dtype=torch.int32, device=self.ctx.device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        self.step = 0
+        self._regions = [(C.c_void_p * world)() for _ in range(2)]
+        self._counts = [(C.c_void_p * world)() for _ in range(2)]
+        for parity in range(2):
+            for d in range(world):
+                self._regions[parity][d] = self.peers[parity][d] + self.HEADER + rank * self.region_bytes
+                self._counts[parity][d] = self.peers[parity][d] + 4 * rank
+
+    def route(self):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        from .runtime import _ptr, _stream
+        if self.world == 1:
+            return
+        par = self.step & 1
+        self.step += 1
+        _lib.check(self.lib.t3d_tsdf_route_export_p2p(self.vol.handle, self.AXIS, self.slab_blocks, self.world, self.rank,
+                                                      self._regions[par], self._counts[par], self.region_records,
+                                                      _ptr(self.fill), _stream()))
+        dist.all_reduce(self.token, group=self.group)     # every rank's export precedes every rank's merge
+        base = self.local[par]
+        for s in range(self.world):
+            if s != self.rank:
+                _lib.check(self.lib.t3d_tsdf_merge_records_dev(
+                    self.vol.handle, C.c_void_p(base + self.HEADER + s * self.region_bytes), C.c_void_p(base + 4 * s),
+                    self.region_records, _stream()))
+        _lib.check(self.lib.t3d_memset_async(C.c_void_p(base), 0, self.HEADER, _stream()))
+
+    def stats(self):
+        """(records sent per destination, records that did not fit) of the last route — synchronises."""
+        f = self.fill.cpu().tolist()
+        sent = [f[d] if d != self.rank else 0 for d in range(self.world)]
+        return sent, f[self.world + 1]
+
+    def close(self):
+        for parity in range(2):
+            for d in range(self.world):
+                if d != self.rank:
+                    self.lib.t3d_ipc_close(self.ctx.handle, self.peers[parity][d])
+            self.lib.t3d_ipc_free(self.ctx.handle, self.local[parity])
+        self.peers, self.local = [], []
+
+
 def allreduce_normal_equations(acc27, sum_d2, count, device=None, group=None):
     """ICP across ranks: every rank linearises its shard of source points
     (Context.icp_linearize), then the 29 sums are all-reduced and every rank solves the
