@@ -49,9 +49,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
         objs.append(obj)
+        headers = list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "t3d.h"]
         if (not force and obj.exists() and obj.stat().st_mtime > src.stat().st_mtime
-                and obj.stat().st_mtime > (CSRC / "common.cuh").stat().st_mtime
-                and obj.stat().st_mtime > (PKG_DIR.parent / "include" / "t3d.h").stat().st_mtime):
+                and all(obj.stat().st_mtime > hdr.stat().st_mtime for hdr in headers)):
             continue
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -51,11 +51,14 @@ __device__ __forceinline__ unsigned long long cell_slot_insert(unsigned long lon
 // boundaries of the sorted key array -> hash of [start, end)
 __global__ void cell_ranges_kernel(const unsigned long long* __restrict__ keys, long long n,
                                    unsigned long long* hkeys, unsigned* hstart, unsigned* hend,
-                                   unsigned long long hmask) {
+                                   unsigned long long hmask, unsigned long long* n_cells) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
-    if (i == 0 || keys[i - 1] != k) hstart[cell_slot_insert(hkeys, hmask, k)] = (unsigned)i;
+    if (i == 0 || keys[i - 1] != k) {
+      hstart[cell_slot_insert(hkeys, hmask, k)] = (unsigned)i;
+      if (n_cells) atomicAdd(n_cells, 1ull);
+    }
     if (i == n - 1 || keys[i + 1] != k) hend[cell_slot_insert(hkeys, hmask, k)] = (unsigned)(i + 1);
   }
 }
@@ -68,18 +71,11 @@ int ceil_log2(long long v) {
 
 }  // namespace
 
-int t3d_grid_build(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, double h,
-                   GridDev* out, cudaStream_t st) {
-  T3D_REQUIRE(n > 0 && n < (1ll << 31), "grid: n=%lld out of range", n);
-  double mn[3], mx[3];
-  int rc = t3d_bounds(ctx, xyz, is_f64, n, mn, mx, reinterpret_cast<t3d_stream>(st));
-  if (rc != T3D_OK) return rc;
-  for (int c = 0; c < 3; ++c) {
-    if (!isfinite(mn[c]) || !isfinite(mx[c])) {
-      t3d_set_error("grid: non-finite coordinates");
-      return T3D_E_NUMERIC;
-    }
-  }
+// One build with a given cell size (h <= 0: density heuristic).  mn/mx: bounds of the cloud.
+// n_cells_h (nullable): receives the number of occupied cells (costs one host sync).
+static int grid_build_once(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, double h, const double* mn,
+                           const double* mx, GridDev* out, long long* n_cells_h, cudaStream_t st) {
+  int rc;
   const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
   if (h <= 0.0) {
     // surface-like clouds: spacing ~ diag / sqrt(n); aim for a few points per cell
@@ -141,9 +137,21 @@ int t3d_grid_build(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, doubl
                                                        ctx->scratch[4].as<float>());
   T3D_LAUNCH_CHECK();
   T3D_CUDA(cudaMemsetAsync(hkeys, 0xFF, hc * 8, st));
-  cell_ranges_kernel<<<grid, 256, 0, st>>>(keys, n, hkeys, hstart, hend, hc - 1);
+  unsigned long long* d_cells = nullptr;
+  if (n_cells_h) {
+    if ((rc = ctx->scratch[11].reserve(64)) != T3D_OK) return rc;
+    d_cells = ctx->scratch[11].as<unsigned long long>();
+    T3D_CUDA(cudaMemsetAsync(d_cells, 0, 8, st));
+  }
+  cell_ranges_kernel<<<grid, 256, 0, st>>>(keys, n, hkeys, hstart, hend, hc - 1, d_cells);
   T3D_LAUNCH_CHECK();
   ctx->launches += 3;
+  if (n_cells_h) {
+    unsigned long long* hp = reinterpret_cast<unsigned long long*>(ctx->pinned) + 512;
+    T3D_CUDA(cudaMemcpyAsync(hp, d_cells, 8, cudaMemcpyDeviceToHost, st));
+    T3D_CUDA(cudaStreamSynchronize(st));
+    *n_cells_h = (long long)*hp;
+  }
   g.sorted_idx = vals;
   g.sorted_xyz = ctx->scratch[4].p;
   g.hkeys = hkeys;
@@ -154,63 +162,103 @@ int t3d_grid_build(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, doubl
   return T3D_OK;
 }
 
+// Builds the index.  h > 0: that cell size.  h <= 0: chosen for a k-nearest search — a density
+// heuristic first, then (target_k > 0) one rebuild if the measured occupancy of the non-empty
+// cells is far from ~target_k/3 points per cell, the point where the 27 cells around a query
+// hold 2-3x k candidates (fewer hash probes per query than with sparse cells, fewer wasted
+// distance evaluations than with crowded ones).  Surface-like clouds: occupancy ~ h^2.
+int t3d_grid_build(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, double h,
+                   GridDev* out, cudaStream_t st, int target_k) {
+  T3D_REQUIRE(n > 0 && n < (1ll << 31), "grid: n=%lld out of range", n);
+  double mn[3], mx[3];
+  int rc = t3d_bounds(ctx, xyz, is_f64, n, mn, mx, reinterpret_cast<t3d_stream>(st));
+  if (rc != T3D_OK) return rc;
+  for (int c = 0; c < 3; ++c) {
+    if (!isfinite(mn[c]) || !isfinite(mx[c])) {
+      t3d_set_error("grid: non-finite coordinates");
+      return T3D_E_NUMERIC;
+    }
+  }
+  if (h > 0.0 || target_k <= 0) return grid_build_once(ctx, xyz, is_f64, n, h, mn, mx, out, nullptr, st);
+  long long cells = 0;
+  rc = grid_build_once(ctx, xyz, is_f64, n, h, mn, mx, out, &cells, st);
+  if (rc != T3D_OK || cells <= 0) return rc;
+  const double occ = (double)n / (double)cells;
+  const double want = target_k / 3.0 > 2.0 ? target_k / 3.0 : 2.0;
+  const double f = sqrt(want / occ);
+  if (f > 0.8 && f < 1.25) return T3D_OK;
+  return grid_build_once(ctx, xyz, is_f64, n, out->h * f, mn, mx, out, nullptr, st);
+}
+
 namespace {
 
 constexpr int KMAX = 32;
 
 // Exact k-nearest search of query q (excluding nothing: the query itself is a
 // neighbour at distance 0, as in Open3D's SearchKNN on its own cloud).
-// Keeps (d2, sorted position) ascending, ties broken by ORIGINAL index.
+// Keeps (d2, sorted position) ascending, ties broken by ORIGINAL index.  The k-entry
+// lists live in shared memory (entry j of thread t at [j * blockDim.x + t]: conflict-free,
+// dynamically indexable); the current k-th distance is mirrored in a register so that the
+// common case — candidate farther than the k-th best — costs no memory access.  Cells whose
+// box is farther than the k-th best are skipped without a hash probe.
 template <typename T>
 __device__ __forceinline__ int knn_search(const GridDev& g, double qx, double qy, double qz,
                                           int k, double* bd, unsigned* bi) {
   const T* pts = reinterpret_cast<const T*>(g.sorted_xyz);
+  const int S = blockDim.x;
   int cx, cy, cz;
   grid_cell_of(g, qx, qy, qz, cx, cy, cz);
   cx = min(max(cx, 0), g.dims[0] - 1);
   cy = min(max(cy, 0), g.dims[1] - 1);
   cz = min(max(cz, 0), g.dims[2] - 1);
   int found = 0;
+  double worst = 1e300;  // bd[k-1] once the list is full
   const int max_ring = max(g.dims[0], max(g.dims[1], g.dims[2]));
-  // distance from q to the faces of its own cell
+  // position of q inside its own cell / distance to its faces
   const double lx = qx - (g.minb[0] + cx * g.h), ly = qy - (g.minb[1] + cy * g.h),
                lz = qz - (g.minb[2] + cz * g.h);
   const double near_face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)),
                                           fmin(lz, g.h - lz)));
   for (int r = 0; r <= max_ring; ++r) {
     for (int dz = -r; dz <= r; ++dz) {
+      const double az = dz == 0 ? 0.0 : (dz < 0 ? lz + (double)(-dz - 1) * g.h : (g.h - lz) + (double)(dz - 1) * g.h);
       for (int dy = -r; dy <= r; ++dy) {
+        const double ay = dy == 0 ? 0.0 : (dy < 0 ? ly + (double)(-dy - 1) * g.h : (g.h - ly) + (double)(dy - 1) * g.h);
         const bool shell_yz = (abs(dz) == r) || (abs(dy) == r);
         const int step = shell_yz ? 1 : 2 * r;  // interior rows: only dx = -r and +r
         for (int dx = -r; dx <= r; dx += (step > 0 ? step : 1)) {
+          const double ax = dx == 0 ? 0.0 : (dx < 0 ? lx + (double)(-dx - 1) * g.h : (g.h - lx) + (double)(dx - 1) * g.h);
+          if (found == k && ax * ax + ay * ay + az * az > worst) continue;  // box farther than the k-th best
           unsigned s, e;
           if (!grid_lookup(g, cx + dx, cy + dy, cz + dz, s, e)) continue;
           for (unsigned j = s; j < e; ++j) {
             const double ddx = (double)pts[3ll * j] - qx, ddy = (double)pts[3ll * j + 1] - qy,
                          ddz = (double)pts[3ll * j + 2] - qz;
             const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (found == k && !(d2 < bd[k - 1] ||
-                                (d2 == bd[k - 1] && g.sorted_idx[j] < g.sorted_idx[bi[k - 1]])))
+            if (found == k && !(d2 < worst ||
+                                (d2 == worst && g.sorted_idx[j] < g.sorted_idx[bi[(k - 1) * S]])))
               continue;
             // insertion (ascending by d2, then by original index)
             int pos = found < k ? found : k - 1;
             const unsigned oj = g.sorted_idx[j];
-            while (pos > 0 && (bd[pos - 1] > d2 ||
-                               (bd[pos - 1] == d2 && g.sorted_idx[bi[pos - 1]] > oj))) {
-              bd[pos] = bd[pos - 1];
-              bi[pos] = bi[pos - 1];
+            while (pos > 0) {
+              const double pd = bd[(pos - 1) * S];
+              if (!(pd > d2 || (pd == d2 && g.sorted_idx[bi[(pos - 1) * S]] > oj))) break;
+              bd[pos * S] = pd;
+              bi[pos * S] = bi[(pos - 1) * S];
               --pos;
             }
-            bd[pos] = d2;
-            bi[pos] = j;
+            bd[pos * S] = d2;
+            bi[pos * S] = j;
             if (found < k) ++found;
+            if (found == k) worst = bd[(k - 1) * S];
           }
         }
       }
     }
     if (found == k) {
       const double reach = near_face + r * g.h;  // everything closer than this has been seen
-      if (bd[k - 1] <= reach * reach) break;
+      if (worst <= reach * reach) break;
     }
     if (r > 0 && cx - r < 0 && cy - r < 0 && cz - r < 0 && cx + r >= g.dims[0] &&
         cy + r >= g.dims[1] && cz + r >= g.dims[2])
@@ -219,17 +267,27 @@ __device__ __forceinline__ int knn_search(const GridDev& g, double qx, double qy
   return found;
 }
 
+constexpr int KNN_THREADS = 128;
+// dynamic shared memory: k doubles + k unsigneds per thread
+__device__ __forceinline__ void knn_lists(int k, double** bd, unsigned** bi) {
+  extern __shared__ double knn_smem[];
+  *bd = knn_smem + threadIdx.x;
+  *bi = reinterpret_cast<unsigned*>(knn_smem + (size_t)k * blockDim.x) + threadIdx.x;
+}
+inline size_t knn_smem_bytes(int k) { return (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(unsigned)); }
+
 // K3: mean distance to the nb nearest neighbours (self included), R3.
 __global__ void __launch_bounds__(128)
     sor_mean_kernel(const __grid_constant__ GridDev g, int nb, double* mean_dist) {
   const double* pts = reinterpret_cast<const double*>(g.sorted_xyz);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
        i += (long long)gridDim.x * blockDim.x) {
-    double bd[KMAX];
-    unsigned bi[KMAX];
+    double* bd;
+    unsigned* bi;
+    knn_lists(nb, &bd, &bi);
     const int found = knn_search<double>(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], nb, bd, bi);
     double sum = 0.0;
-    for (int k = 0; k < found; ++k) sum += sqrt(bd[k]);
+    for (int k = 0; k < found; ++k) sum += sqrt(bd[k * blockDim.x]);
     mean_dist[g.sorted_idx[i]] = found > 0 ? sum / (double)found : -1.0;
   }
 }
@@ -348,15 +406,17 @@ __global__ void __launch_bounds__(128)
   const float* pts = reinterpret_cast<const float*>(g.sorted_xyz);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
        i += (long long)gridDim.x * blockDim.x) {
-    double bd[KMAX];
-    unsigned bi[KMAX];
+    double* bd;
+    unsigned* bi;
+    knn_lists(knn, &bd, &bi);
     const double qx = pts[3 * i], qy = pts[3 * i + 1], qz = pts[3 * i + 2];
     const int found = knn_search<float>(g, qx, qy, qz, knn, bd, bi);
     double n[3] = {0.0, 0.0, 1.0};
     if (found >= 3) {
       double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int k = 0; k < found; ++k) {
-        const double x = pts[3ll * bi[k]], y = pts[3ll * bi[k] + 1], z = pts[3ll * bi[k] + 2];
+        const unsigned jj = bi[k * blockDim.x];
+        const double x = pts[3ll * jj], y = pts[3ll * jj + 1], z = pts[3ll * jj + 2];
         c[0] += x; c[1] += y; c[2] += z;
         c[3] += x * x; c[4] += x * y; c[5] += x * z;
         c[6] += y * y; c[7] += y * z; c[8] += z * z;
@@ -411,7 +471,7 @@ extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t 
   if (n == 0) return T3D_OK;
   T3D_REQUIRE(xyz, "t3d_statistical_outlier: null xyz");
   GridDev g;
-  int rc = t3d_grid_build(ctx, xyz, 1, n, -1.0, &g, st);
+  int rc = t3d_grid_build(ctx, xyz, 1, n, -1.0, &g, st, nb);
   if (rc != T3D_OK) return rc;
   const int grid = ctx->num_sms * 8;
   double* mean = out_mean_dist;
@@ -421,7 +481,7 @@ extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t 
   }
   const long long want = (n + 127) / 128;
   const int mgrid = (int)(want < 2ll * grid ? want : 2ll * grid);
-  sor_mean_kernel<<<mgrid, 128, 0, st>>>(g, nb, mean);
+  sor_mean_kernel<<<mgrid, KNN_THREADS, knn_smem_bytes(nb), st>>>(g, nb, mean);
   T3D_LAUNCH_CHECK();
   // mu, sigma: per-CTA partials summed on the host in a fixed order
   const int sgrid = 256;
@@ -465,11 +525,11 @@ extern "C" int t3d_estimate_normals(t3d_ctx* ctx, const float* xyz, int64_t n, i
   if (n == 0) return T3D_OK;
   cudaStream_t st = as_stream(stream);
   GridDev g;
-  int rc = t3d_grid_build(ctx, xyz, 0, n, -1.0, &g, st);
+  int rc = t3d_grid_build(ctx, xyz, 0, n, -1.0, &g, st, knn);
   if (rc != T3D_OK) return rc;
   const long long want = (n + 127) / 128;
   const int grid = (int)(want < ctx->num_sms * 16 ? want : ctx->num_sms * 16);
-  normals_kernel<<<grid, 128, 0, st>>>(g, knn, orient_to_h != nullptr,
+  normals_kernel<<<grid, KNN_THREADS, knn_smem_bytes(knn), st>>>(g, knn, orient_to_h != nullptr,
                                        orient_to_h ? orient_to_h[0] : 0.0,
                                        orient_to_h ? orient_to_h[1] : 0.0,
                                        orient_to_h ? orient_to_h[2] : 0.0, nrm);
@@ -491,7 +551,7 @@ extern "C" int t3d_nearest_neighbor(t3d_ctx* ctx, const float* query, int64_t n_
     return T3D_OK;
   }
   GridDev g;
-  int rc = t3d_grid_build(ctx, ref, 0, n_ref, radius, &g, st);
+  int rc = t3d_grid_build(ctx, ref, 0, n_ref, radius, &g, st, 0);
   if (rc != T3D_OK) return rc;
   const long long want = (n_q + 127) / 128;
   const int grid = (int)(want < ctx->num_sms * 16 ? want : ctx->num_sms * 16);

@@ -91,7 +91,7 @@ __device__ __forceinline__ int t3d_nn_within(const GridDev& g, double qx, double
 // (h <= 0: pick from the point density).  Buffers live in ctx->scratch[0..5];
 // the GridDev stays valid until the next build on the same ctx.
 int t3d_grid_build(t3d_ctx* ctx, const void* xyz, int is_f64, long long n, double h,
-                   GridDev* out, cudaStream_t st);
+                   GridDev* out, cudaStream_t st, int target_k = 0);
 
 int t3d_radix_sort_u64(t3d_ctx* ctx, unsigned long long* keys_a, unsigned* vals_a,
                        unsigned long long* keys_b, unsigned* vals_b, long long n,
