@@ -361,53 +361,13 @@ __device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int
   }
 }
 
-// Phase 1 (per thread): rings 0 and 1 (27 cells).  Returns true when the result is final.
-// The 8 cells of the query's octant (its own cell and the neighbours on the side of the
-// cell the query sits in) are probed first: with h ~ 2-3 surface samples they almost
-// always hold the nearest neighbour, after which the other 19 cells are rejected by the
-// box-distance test alone (no memory access).  Every lane of a warp runs the same 8-probe
-// sequence, so the octant pass is divergence-free.
-__device__ __forceinline__ bool hg_nn_near(const HGrid& g, double qx, double qy, double qz, double r2,
-                                           int cx, int cy, int cz, double lx, double ly, double lz,
-                                           NNState& st) {
-  const double face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)), fmin(lz, g.h - lz)));
-  const double hh = 0.5 * g.h;
-  const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
-#pragma unroll 1
-  for (int o = 0; o < 8; ++o) {
-    const int dx = (o & 1) ? ox : 0, dy = (o & 2) ? oy : 0, dz = (o & 4) ? oz : 0;
-    if (o != 0 && hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
-    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
-  }
-#pragma unroll 1
-  for (int i = 1; i < 27; ++i) {
-    const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
-    if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
-    if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
-    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
-  }
-  // after rings 0+1 everything closer than h + face has been seen
-  const double reach1 = g.h + face;
-  return st.best <= reach1 * reach1;
-}
-
-// Phase 2 (whole warp, one query at a time): the 98 cells of ring 2 are probed 32 at a
-// time — the long tail of queries without a close neighbour costs 4 parallel probe
-// rounds instead of 98 dependent ones.  Ends with a warp arg-min (d2, then index).
-__device__ __forceinline__ void hg_nn_far_warp(const HGrid& g, double qx, double qy, double qz, double r2,
-                                               int cx, int cy, int cz, double lx, double ly, double lz,
-                                               NNState& st, unsigned lane) {
-#pragma unroll 1
-  for (int i = 27 + (int)lane; i < 125; i += 32) {
-    const int dx = c_ofs[i][0], dy = c_ofs[i][1], dz = c_ofs[i][2];
-    if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > st.best) continue;
-    hg_scan_cell(g, cx + dx, cy + dy, cz + dz, qx, qy, qz, r2, st);
-  }
+// (d2, original index) arg-min across the 8 lanes of a query group
+__device__ __forceinline__ void nn_group_min(NNState& st, unsigned gmask) {
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, st.best, d);
-    const int oj = __shfl_xor_sync(0xffffffffu, st.bj, d);
-    const unsigned oo = __shfl_xor_sync(0xffffffffu, st.bo, d);
+  for (int d = 4; d > 0; d >>= 1) {
+    const double ob = __shfl_xor_sync(gmask, st.best, d);
+    const int oj = __shfl_xor_sync(gmask, st.bj, d);
+    const unsigned oo = __shfl_xor_sync(gmask, st.bo, d);
     if (oj >= 0 && (st.bj < 0 || ob < st.best || (ob == st.best && oo < st.bo))) {
       st.best = ob; st.bj = oj; st.bo = oo;
     }
@@ -475,7 +435,16 @@ struct IcpState {       // device-resident registration state (also the D2H resu
 //                   last CTA to finish sums the per-CTA partials in blockIdx order
 //                   (deterministic), checks convergence and solves the 6x6 system.
 constexpr int NN_THREADS = 256;
+constexpr int NN_GROUP = 8;  // lanes per query
 
+// Exact nearest neighbour, EIGHT lanes per query (the clouds of one frame hold ~1e5 queries:
+// one thread per query leaves the GPU short of warps and gives every warp a long dependent
+// chain of hash probes).  Step 1: the 8 lanes probe the 8 cells of the query's octant (its own
+// cell and the neighbours on the side the query sits in) at once — with h ~ 2-3 surface
+// samples these almost always contain the answer.  Step 2: the other 19 cells of ring 1 are
+// dealt round-robin; a cell is probed only if its box is closer than the best so far.
+// Step 3 (rare): ring 2 the same way, only if something closer could still hide there.
+// Between steps the group takes an arg-min over (d2, original index) with 3 shuffles.
 __global__ void __launch_bounds__(NN_THREADS, 4)
     icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
                   double r2, const IcpState* st, int* __restrict__ corr, double* __restrict__ corr_d2) {
@@ -484,54 +453,54 @@ __global__ void __launch_bounds__(NN_THREADS, 4)
   if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
   __syncthreads();
   const unsigned l = lane_id();
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - l; base < n_src;
-       base += (long long)gridDim.x * blockDim.x) {  // warp-uniform trip count
-    const long long i = base + l;
-    const bool valid = i < n_src;
-    double sx = 0.0, sy = 0.0, sz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
-    int cx = 0, cy = 0, cz = 0;
+  const unsigned grp = l / NN_GROUP, sub = l % NN_GROUP;
+  const unsigned gmask = 0xFFu << (grp * NN_GROUP);
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int QPW = 32 / NN_GROUP;  // queries per warp
+  for (long long qb = warp_global * QPW; qb < n_src; qb += total_warps * QPW) {
+    const long long i = qb + grp;
+    if (i >= n_src) continue;  // group-uniform
+    const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+    const double sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+    const double sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+    const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
     NNState nn;
     nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
-    bool final_ = true;
-    if (valid) {
-      const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
-      sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
-      sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
-      sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
-      if (hg_cell(g, sx, sy, sz, cx, cy, cz) && hg_near_target(g, cx, cy, cz)) {
-        lx = sx - (double)cx * g.h; ly = sy - (double)cy * g.h; lz = sz - (double)cz * g.h;
-        final_ = hg_nn_near(g, sx, sy, sz, r2, cx, cy, cz, lx, ly, lz, nn);
+    int cx, cy, cz;
+    if (hg_cell(g, sx, sy, sz, cx, cy, cz) && hg_near_target(g, cx, cy, cz)) {  // group-uniform
+      const double lx = sx - (double)cx * g.h, ly = sy - (double)cy * g.h, lz = sz - (double)cz * g.h;
+      const double hh = 0.5 * g.h;
+      const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
+      {  // step 1: one octant cell per lane
+        const int dx = (sub & 1) ? ox : 0, dy = (sub & 2) ? oy : 0, dz = (sub & 4) ? oz : 0;
+        if (sub == 0 || hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) <= nn.best)
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
       }
-    }
-    // queries that still need ring 2.  Few per warp: the warp serves them one at a time,
-    // 32 cells per step.  Many (spatially coherent misses): every lane walks its own ring 2.
-    unsigned need = __ballot_sync(0xffffffffu, !final_);
-    if (__popc(need) > 6) {
-      if (!final_) {
+      nn_group_min(nn, gmask);
+      // step 2: the rest of ring 1
 #pragma unroll 1
-        for (int c = 27; c < 125; ++c) {
+      for (int c = 1 + (int)sub; c < 27; c += NN_GROUP) {
+        const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
+        if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
+        if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > nn.best) continue;
+        hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
+      }
+      nn_group_min(nn, gmask);
+      // after rings 0+1 everything closer than h + (distance of q to its cell's faces) has been seen
+      const double face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)), fmin(lz, g.h - lz)));
+      const double reach1 = g.h + face;
+      if (!(nn.best <= reach1 * reach1)) {  // step 3: ring 2 (group-uniform branch)
+#pragma unroll 1
+        for (int c = 27 + (int)sub; c < 125; c += NN_GROUP) {
           const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
           if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > nn.best) continue;
           hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
         }
+        nn_group_min(nn, gmask);
       }
-      need = 0;
     }
-    while (need) {
-      const int L = __ffs(need) - 1;
-      need &= need - 1;
-      NNState q;
-      q.best = __shfl_sync(0xffffffffu, nn.best, L);
-      q.bj = __shfl_sync(0xffffffffu, nn.bj, L);
-      q.bo = __shfl_sync(0xffffffffu, nn.bo, L);
-      hg_nn_far_warp(g, __shfl_sync(0xffffffffu, sx, L), __shfl_sync(0xffffffffu, sy, L),
-                     __shfl_sync(0xffffffffu, sz, L), r2, __shfl_sync(0xffffffffu, cx, L),
-                     __shfl_sync(0xffffffffu, cy, L), __shfl_sync(0xffffffffu, cz, L),
-                     __shfl_sync(0xffffffffu, lx, L), __shfl_sync(0xffffffffu, ly, L),
-                     __shfl_sync(0xffffffffu, lz, L), q, l);
-      if ((int)l == L) nn = q;
-    }
-    if (valid) {
+    if (sub == 0) {
       corr[i] = nn.bj;
       corr_d2[i] = nn.best;
     }
@@ -700,7 +669,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   g.n = n_tgt;
   const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
   const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * 4 ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * 4);
-  const long long want_nn = (n_src + NN_THREADS - 1) / NN_THREADS;
+  const long long want_nn = (n_src * NN_GROUP + NN_THREADS - 1) / NN_THREADS;
   const int grid_nn = (int)(want_nn < (long long)ctx->num_sms * 8 ? (want_nn > 0 ? want_nn : 1) : (long long)ctx->num_sms * 8);
   if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid_acc * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
   double* partial = ctx->scratch[6].as<double>();
