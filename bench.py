@@ -568,6 +568,8 @@ def main():
             args.block_capacity = 1_500_000
         if args.cpu_frames == 300:
             args.cpu_frames = 8
+        if args.region_records == 16384:
+            args.region_records = 65536       # 4x more blocks per metre of look-ahead than cfg2
     if args.impl == "reference":
         run_reference(args)
     else:
