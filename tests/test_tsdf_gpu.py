@@ -318,3 +318,35 @@ def test_multi_gpu_routers_agree():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tests" / "mgpu_route_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "p2p==nccl True owned==serial True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_full_size_tracking_properties(ctx):
+    """cfg-3 at BASELINE frame size (1080x1920, 0.25 m/frame): the tracker stays on the ground-truth
+    trajectory, its poses are rigid, and with known poses it reproduces plain integration."""
+    import torch
+    from textureless_3d_reconstruction_b200.tracking import FrameToModelTracker
+    H, W = 1920, 1080
+    K = (1719.0, 1719.0, 540.0, 960.0)
+    n = 16
+    fr = [ctx.synth_frame(0, i, H, W, *K, noise_sigma=0.002) for i in range(n)]
+    trk = FrameToModelTracker(K, H, W, block_capacity=120000, icp_subsample=4, icp_max_corr=0.05, ctx=ctx)
+    for i, (d, c, T) in enumerate(fr):
+        trk.add_frame(d, c, known_pose=T if i == 0 else None)
+    for i in range(n):
+        P = trk.poses[i]
+        assert np.allclose(P[:3, :3] @ P[:3, :3].T, np.eye(3), atol=1e-9) and abs(np.linalg.det(P[:3, :3]) - 1) < 1e-9
+        G = np.eye(4)
+        G[:3, :4] = fr[i][2]
+        E = P @ np.linalg.inv(G)
+        assert np.linalg.norm(E[:3, 3]) < 0.02, (i, E[:3, 3])              # < 2 cm after up to 3.75 m of travel
+        assert np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)) < 5e-3
+    log = [r for r in trk.icp_log if r is not None]
+    assert len(log) == n - 1 and all(r.fitness > 0.8 and r.inlier_rmse < 0.02 and r.iterations <= 30 for r in log)
+    # known poses through the same class == TSDFVolume.integrate
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    a = FrameToModelTracker(K, H, W, block_capacity=60000, ctx=ctx)
+    b = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    for d, c, T in fr[:3]:
+        a.add_frame(d, c, known_pose=T)
+        b.integrate(d, c, K, T, 1.0, 5.0)
+    assert a.volume.counters() == b.counters() and a.volume.num_blocks == b.num_blocks
