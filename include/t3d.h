@@ -330,7 +330,9 @@ typedef struct t3d_icp_result {
 } t3d_icp_result;
 
 /* src: n_src*3 f32; tgt, tgt_nrm: n_tgt*3 f32.  T0_h: host row-major 4x4.
- * Synchronous (per-iteration 6x6 solve on the host in f64). */
+ * The whole registration runs on the device (correspondences, f64 normal equations,
+ * 6x6 solve with the R8 determinant guard, convergence test); the host reads one result
+ * record.  Synchronous. */
 int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_src,
                            const float* tgt, const float* tgt_nrm,
                            int64_t n_tgt, double max_corr_dist,

@@ -86,59 +86,7 @@ __global__ void icp_final_kernel(const double* partial, int nblocks, double* out
   out29[k] = t;
 }
 
-// ---- host 6x6 helpers -----------------------------------------------------
-__host__ __device__ double det6(const double* A) {
-  double M[36];
-  for (int i = 0; i < 36; ++i) M[i] = A[i];
-  double det = 1.0;
-  for (int c = 0; c < 6; ++c) {
-    int p = c;
-    for (int r = c + 1; r < 6; ++r)
-      if (fabs(M[r * 6 + c]) > fabs(M[p * 6 + c])) p = r;
-    if (M[p * 6 + c] == 0.0) return 0.0;
-    if (p != c) {
-      for (int k = 0; k < 6; ++k) { double t = M[c * 6 + k]; M[c * 6 + k] = M[p * 6 + k]; M[p * 6 + k] = t; }
-      det = -det;
-    }
-    det *= M[c * 6 + c];
-    for (int r = c + 1; r < 6; ++r) {
-      const double f = M[r * 6 + c] / M[c * 6 + c];
-      for (int k = c; k < 6; ++k) M[r * 6 + k] -= f * M[c * 6 + k];
-    }
-  }
-  return det;
-}
-
-// LDL^T solve of the symmetric system A x = b (no pivoting; A is PSD here)
-__host__ __device__ bool ldlt_solve6(const double* A, const double* b, double* x) {
-  double L[36] = {0}, D[6];
-  for (int j = 0; j < 6; ++j) {
-    double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
-    D[j] = d;
-    if (d == 0.0 || !isfinite(d)) return false;
-    L[j * 6 + j] = 1.0;
-    for (int i = j + 1; i < 6; ++i) {
-      double v = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
-      L[i * 6 + j] = v / d;
-    }
-  }
-  double y[6];
-  for (int i = 0; i < 6; ++i) {
-    double v = b[i];
-    for (int k = 0; k < i; ++k) v -= L[i * 6 + k] * y[k];
-    y[i] = v;
-  }
-  for (int i = 0; i < 6; ++i) y[i] /= D[i];
-  for (int i = 5; i >= 0; --i) {
-    double v = y[i];
-    for (int k = i + 1; k < 6; ++k) v -= L[k * 6 + i] * x[k];
-    x[i] = v;
-  }
-  return true;
-}
-
+// ---- small matrix helpers (host + device) ----------------------------------
 __host__ __device__ void mat4_mul(const double* A, const double* B, double* C) {
   double R[16];
   for (int i = 0; i < 4; ++i)
@@ -158,25 +106,6 @@ __host__ __device__ void vec6_to_mat4(const double* x, double* M) {
   M[4] = sg * cb; M[5] = sg * sb * sa + cg * ca; M[6] = sg * sb * ca - cg * sa; M[7] = x[4];
   M[8] = -sb;     M[9] = cb * sa;                M[10] = cb * ca;               M[11] = x[5];
   M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
-}
-
-// solve the normal equations -> update matrix (identity when ill-posed, R8)
-__host__ __device__ void solve_update(const double* acc, double* U) {
-  double A[36], b[6], x[6];
-  int q = 0;
-  for (int a = 0; a < 6; ++a)
-    for (int c = a; c < 6; ++c) { A[a * 6 + c] = acc[q]; A[c * 6 + a] = acc[q]; ++q; }
-  for (int a = 0; a < 6; ++a) b[a] = -acc[21 + a];
-  const double det = det6(A);
-  bool ok = isfinite(det) && fabs(det) >= 1e-6;
-  if (ok) ok = ldlt_solve6(A, b, x);
-  if (ok)
-    for (int a = 0; a < 6; ++a) ok = ok && isfinite(x[a]);
-  if (!ok) {
-    for (int i = 0; i < 16; ++i) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    return;
-  }
-  vec6_to_mat4(x, U);
 }
 
 int linearize(t3d_ctx* ctx, const GridDev& g, const float* src, long long n_src,
@@ -222,6 +151,7 @@ struct HGrid {            // cells of size h keyed by floor(p / h) (biased 21-bi
   unsigned* count;        // points in the cell
   unsigned* start;        // first sorted position of the cell
   unsigned* fill;         // scatter cursor
+  unsigned long long* coarse_keys;  // set of occupied coarse cells (input of the dilation)
   unsigned long long* near_keys;  // set of coarse cells (2h = max_corr) with a target within one coarse
                                   // cell in every direction: a query whose coarse cell is absent has no
                                   // correspondence — decided by ONE probe instead of 125
@@ -270,10 +200,31 @@ __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
     const unsigned c = g.count[s];
     if (!c) continue;
     g.start[s] = atomicAdd(g.cursor, c);
-    // mark the 27 coarse cells around this fine cell's coarse cell
+    // note this fine cell's coarse cell (2h); hg_dilate_kernel then marks the 27 coarse cells around
+    // every occupied coarse cell — one dilation per coarse cell instead of one per fine cell
     int fx, fy, fz;
     unpack_key(g.keys[s], fx, fy, fz);
-    const int qx = fx >> 1, qy = fy >> 1, qz = fz >> 1;
+    const unsigned long long key = pack_key(fx >> 1, fy >> 1, fz >> 1);
+    unsigned long long slot = mix64(key) & g.mask;
+    while (true) {
+      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(g.coarse_keys + slot));
+      if (k == key) break;
+      if (k == T3D_KEY_EMPTY) {
+        k = atomicCAS(g.coarse_keys + slot, T3D_KEY_EMPTY, key);
+        if (k == T3D_KEY_EMPTY || k == key) break;
+      }
+      slot = (slot + 1) & g.mask;
+    }
+  }
+}
+
+__global__ void hg_dilate_kernel(const __grid_constant__ HGrid g) {
+  for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s <= g.mask;
+       s += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long ck = g.coarse_keys[s];
+    if (ck == T3D_KEY_EMPTY) continue;
+    int qx, qy, qz;
+    unpack_key(ck, qx, qy, qz);
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
@@ -633,7 +584,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   unsigned long long hc = 1024;
   while (hc < 2ull * (unsigned long long)n_tgt) hc <<= 1;
   int rc;
-  if ((rc = ctx->scratch[0].reserve(hc * 28)) != T3D_OK) return rc;
+  if ((rc = ctx->scratch[0].reserve(hc * 36)) != T3D_OK) return rc;
   if ((rc = ctx->scratch[1].reserve((size_t)n_tgt * 28 + 64)) != T3D_OK) return rc;
   static bool ofs_ready = false;
   if (!ofs_ready) {  // 5^3 offsets sorted by (ring, squared length)
@@ -661,6 +612,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   g.start = g.count + hc;
   g.fill = g.start + hc;
   g.near_keys = reinterpret_cast<unsigned long long*>(g.fill + hc);
+  g.coarse_keys = g.near_keys + hc;
   g.mask = hc - 1;
   g.xyzi = ctx->scratch[1].as<float4>();
   g.nrm = reinterpret_cast<float*>(g.xyzi + n_tgt);
@@ -683,16 +635,18 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
 
   T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
   T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
-  T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 8, st));
+  T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
   T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
   const int bgrid = (int)((n_tgt + 255) / 256 < (long long)ctx->num_sms * 8 ? (n_tgt + 255) / 256 : (long long)ctx->num_sms * 8);
   hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
   T3D_LAUNCH_CHECK();
   hg_alloc_kernel<<<(int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368), 256, 0, st>>>(g);
   T3D_LAUNCH_CHECK();
+  hg_dilate_kernel<<<(int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368), 256, 0, st>>>(g);
+  T3D_LAUNCH_CHECK();
   hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
   T3D_LAUNCH_CHECK();
-  ctx->launches += 3;
+  ctx->launches += 4;
 
   IcpState* hst = reinterpret_cast<IcpState*>(reinterpret_cast<char*>(ctx->pinned) + 2048);
   unsigned* hflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + 1024);
@@ -769,38 +723,6 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
   if (n_src == 0 || n_tgt == 0) return T3D_OK;
   T3D_REQUIRE(src && tgt && tgt_nrm, "t3d_icp_point_to_plane: null clouds");
   cudaStream_t st = as_stream(stream);
-  static int host_loop = -1;  // debug knob: T3D_ICP_HOSTLOOP=1 -> per-iteration host loop over the sorted grid
-  if (host_loop < 0) host_loop = getenv("T3D_ICP_HOSTLOOP") ? 1 : 0;
-  if (!host_loop)
-    return icp_fused(ctx, src, n_src, tgt, tgt_nrm, n_tgt, max_corr_dist, res->T, max_iter, rel_fitness,
-                     rel_rmse, res, st);
-  GridDev g;
-  int rc = t3d_grid_build(ctx, tgt, 0, n_tgt, max_corr_dist, &g, st);
-  if (rc != T3D_OK) return rc;
-  double acc[NACC];
-  rc = linearize(ctx, g, src, n_src, tgt_nrm, max_corr_dist, res->T, acc, st);
-  if (rc != T3D_OK) return rc;
-  double fitness = acc[28] / (double)n_src;
-  double rmse = acc[28] > 0.0 ? sqrt(acc[27] / acc[28]) : 0.0;
-  int it = 0;
-  int converged = 0;
-  for (; it < max_iter; ++it) {
-    double U[16];
-    solve_update(acc, U);
-    mat4_mul(U, res->T, res->T);
-    rc = linearize(ctx, g, src, n_src, tgt_nrm, max_corr_dist, res->T, acc, st);
-    if (rc != T3D_OK) return rc;
-    const double f2 = acc[28] / (double)n_src;
-    const double r2 = acc[28] > 0.0 ? sqrt(acc[27] / acc[28]) : 0.0;
-    const bool stop = fabs(fitness - f2) < rel_fitness && fabs(rmse - r2) < rel_rmse;
-    fitness = f2;
-    rmse = r2;
-    if (stop) { converged = 1; ++it; break; }
-  }
-  res->fitness = fitness;
-  res->inlier_rmse = rmse;
-  res->iterations = it;
-  res->converged = converged;
-  res->correspondences = (int64_t)acc[28];
-  return T3D_OK;
+  return icp_fused(ctx, src, n_src, tgt, tgt_nrm, n_tgt, max_corr_dist, res->T, max_iter, rel_fitness,
+                   rel_rmse, res, st);
 }
