@@ -523,7 +523,7 @@ def run_cfg3(args):
                          "max_translation_error_m": max(e[0] for e in errs), "trajectory_length_m": 0.25 * (F - 1),
                          "mean_icp_iterations": float(np.mean(its)) if its else None,
                          "mean_fitness": float(np.mean(fit)) if fit else None,
-                         "last_target_points_blocks": list(trk.last_target)},
+                         "last_target_points": trk.last_target[0]},
             "cpu_baseline": cpu, "blocks": int(nblocks)}
     print(json.dumps(line), flush=True)
 

@@ -299,8 +299,9 @@ int t3d_tsdf_extract_points(t3d_tsdf* v, float weight_threshold, float* xyz,
  * the ICP target is the model surface inside the predicted view).  A block is
  * kept iff its bounding sphere (centre (key+0.5)*8*voxel, radius sqrt(3)/2*8*voxel)
  * reaches into depth (0, depth_max) and into the image rectangle of view_h
- * (K, T_cw; depth/bgr pointers ignored).  out_blocks_h (nullable, host): number
- * of blocks selected.  Synchronous (block count). */
+ * (K, T_cw; depth/bgr pointers ignored).  Asynchronous — block and point counts stay on
+ * the device — unless out_blocks_h (nullable, host: number of blocks selected) is given,
+ * which costs one stream synchronisation.  If *out_n > capacity the output was truncated. */
 int t3d_tsdf_extract_points_view(t3d_tsdf* v, const t3d_frame_view* view_h, int H,
                                  int W, float depth_max, float weight_threshold,
                                  float* xyz, float* nrm, uint8_t* rgb,
@@ -339,6 +340,19 @@ int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_src,
                            const double* T0_h, int max_iter,
                            double rel_fitness, double rel_rmse,
                            t3d_icp_result* result_h, t3d_stream stream);
+
+/* Same registration with the cloud sizes in DEVICE memory (int64): src/tgt buffers hold up
+ * to src_capacity / tgt_capacity points, of which *n_src_dev / *n_tgt_dev are valid.  Made for
+ * frame-to-model tracking, where both clouds were just produced on the device (K1, K6): their
+ * sizes never visit the host.  If either cloud has fewer than min_points points no registration
+ * is attempted: T = T0 and *skipped_h = 1. */
+int t3d_icp_point_to_plane_dev(t3d_ctx* ctx, const float* src, int64_t src_capacity,
+                               const int64_t* n_src_dev, const float* tgt,
+                               const float* tgt_nrm, int64_t tgt_capacity,
+                               const int64_t* n_tgt_dev, int min_points,
+                               double max_corr_dist, const double* T0_h, int max_iter,
+                               double rel_fitness, double rel_rmse,
+                               t3d_icp_result* result_h, int* skipped_h, t3d_stream stream);
 
 /* One ICP linearisation: correspondences + 6x6 normal equations only.
  * out27_h: 21 upper-triangular JtJ + 6 Jtr; out_stats_h: sum r^2 (squared

@@ -103,6 +103,8 @@ _SIGS = {
     "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),
     "t3d_icp_point_to_plane": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _I, _D, _D, C.POINTER(IcpResult), _VP]),
+    "t3d_icp_point_to_plane_dev": (_I, [_VP, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I, _D, _VP, _I, _D, _D,
+                                        C.POINTER(IcpResult), C.POINTER(C.c_int), _VP]),
     "t3d_icp_linearize": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _VP, _VP, _VP]),
     "t3d_nearest_neighbor": (_I, [_VP, _VP, _I64, _VP, _I64, _D, _VP, _VP, _VP]),
     "t3d_depth_u16_to_f32": (_I, [_VP, _VP, _I64, _F, _VP, _VP]),

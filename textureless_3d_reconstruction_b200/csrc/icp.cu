@@ -160,8 +160,15 @@ struct HGrid {            // cells of size h keyed by floor(p / h) (biased 21-bi
   float* nrm;             // n*3, same order
   unsigned* cursor;       // [0] running start allocator, [1] out-of-range flag
   double inv_h, h;        // cell size h = max_corr / 2: the search covers the 5^3 cells around the query
-  long long n;
+  long long n;            // number of target points (upper bound when n_dev is set)
+  const long long* n_dev; // nullable: actual count lives in device memory (no host sync)
 };
+
+__device__ __forceinline__ long long hg_n(const HGrid& g) {
+  if (!g.n_dev) return g.n;
+  const long long v = *g.n_dev;
+  return v < g.n ? v : g.n;
+}
 
 // 5x5x5 cell offsets ordered by ring (max-norm) and, inside a ring, by distance:
 // ring 0 = 1 cell, ring 1 = 26, ring 2 = 98.
@@ -176,7 +183,8 @@ __device__ __forceinline__ bool hg_cell(const HGrid& g, double x, double y, doub
 }
 
 __global__ void hg_count_kernel(const float* __restrict__ tgt, const __grid_constant__ HGrid g) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+  const long long n = hg_n(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int cx, cy, cz;
     if (!hg_cell(g, tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2], cx, cy, cz)) { g.cursor[1] = 1; continue; }
@@ -256,7 +264,8 @@ __device__ __forceinline__ bool hg_near_target(const HGrid& g, int cx, int cy, i
 
 __global__ void hg_scatter_kernel(const float* __restrict__ tgt, const float* __restrict__ tgt_nrm,
                                   const __grid_constant__ HGrid g) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+  const long long n = hg_n(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int cx, cy, cz;
     const float x = tgt[3 * i], y = tgt[3 * i + 1], z = tgt[3 * i + 2];
@@ -374,7 +383,8 @@ struct IcpState {       // device-resident registration state (also the D2H resu
   double fitness, rmse;
   double acc[NACC];     // last linearisation
   int iterations, converged, done, round;
-  unsigned ticket, pad;
+  unsigned ticket;
+  int skipped;          // device-count mode: a cloud was smaller than min_points
 };
 
 // One linearisation = two launches, both of which return at once when the
@@ -398,8 +408,10 @@ constexpr int NN_GROUP = 8;  // lanes per query
 // Between steps the group takes an arg-min over (d2, original index) with 3 shuffles.
 __global__ void __launch_bounds__(NN_THREADS, 4)
     icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
-                  double r2, const IcpState* st, int* __restrict__ corr, double* __restrict__ corr_d2) {
+                  const long long* n_src_dev, double r2, const IcpState* st, int* __restrict__ corr,
+                  double* __restrict__ corr_d2) {
   if (*reinterpret_cast<const volatile int*>(&st->done)) return;
+  if (n_src_dev) { const long long v = *n_src_dev; n_src = v < n_src ? v : n_src; }
   __shared__ double s_T[12];
   if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
   __syncthreads();
@@ -460,10 +472,11 @@ __global__ void __launch_bounds__(NN_THREADS, 4)
 
 __global__ void __launch_bounds__(ICP_THREADS)
     icp_acc_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
-                   int max_iter, double rel_fitness, double rel_rmse, IcpState* st,
-                   const int* __restrict__ corr, const double* __restrict__ corr_d2,
+                   const long long* n_src_dev, int min_points, int max_iter, double rel_fitness, double rel_rmse,
+                   IcpState* st, const int* __restrict__ corr, const double* __restrict__ corr_d2,
                    double* partial /* gridDim.x * NACC */) {
   if (*reinterpret_cast<volatile int*>(&st->done)) return;
+  if (n_src_dev) { const long long v = *n_src_dev; n_src = v < n_src ? v : n_src; }
   __shared__ double s[ICP_THREADS / 32][NACC];
   __shared__ double s_T[12];
   __shared__ unsigned s_last;
@@ -551,11 +564,15 @@ __global__ void __launch_bounds__(ICP_THREADS)
       done = true;
     }
     if (!done && round >= max_iter) done = true;
+    // device-count mode: clouds below min_points are not registered (pose = initial guess)
+    const bool skipped = min_points > 0 && (n_src < min_points || hg_n(g) < min_points);
+    if (skipped) done = true;
     double x[6] = {0, 0, 0, 0, 0, 0};
     bool solved = false;
     if (!done) solved = warp_solve6(st->acc, x, l);
     __syncwarp();
     if (l == 0) {
+      if (skipped) st->skipped = 1;
       if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
       if (converged) st->converged = 1;
       st->fitness = f2;
@@ -577,9 +594,13 @@ __global__ void __launch_bounds__(ICP_THREADS)
 
 }  // namespace
 
-static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float* tgt, const float* tgt_nrm,
-                     int64_t n_tgt, double max_corr, const double* T0, int max_iter, double rel_fitness,
-                     double rel_rmse, t3d_icp_result* res, cudaStream_t st) {
+// n_src / n_tgt are exact counts, or capacities when n_src_dev / n_tgt_dev point at the actual
+// counts in device memory (frame-to-model tracking: the clouds were just produced on the device and
+// their sizes never visit the host).
+static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long long* n_src_dev, const float* tgt,
+                     const float* tgt_nrm, int64_t n_tgt, const long long* n_tgt_dev, int min_points,
+                     double max_corr, const double* T0, int max_iter, double rel_fitness,
+                     double rel_rmse, t3d_icp_result* res, int* skipped_h, cudaStream_t st) {
   T3D_REQUIRE(n_tgt < (1ll << 31) && n_src < (1ll << 40), "icp: cloud too large");
   unsigned long long hc = 1024;
   while (hc < 2ull * (unsigned long long)n_tgt) hc <<= 1;
@@ -619,6 +640,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   g.h = max_corr * 0.5;
   g.inv_h = 1.0 / g.h;
   g.n = n_tgt;
+  g.n_dev = n_tgt_dev;
   const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
   const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * 4 ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * 4);
   const long long want_nn = (n_src * NN_GROUP + NN_THREADS - 1) / NN_THREADS;
@@ -662,9 +684,9 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
     int n = max_iter + 1 - enqueued;
     if (n > chunk) n = chunk;
     for (int r = 0; r < n; ++r) {
-      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, r2, dst, corr, corr_d2);
-      icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, max_iter, rel_fitness,
-                                                        rel_rmse, dst, corr, corr_d2, partial);
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2);
+      icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, min_points, max_iter,
+                                                        rel_fitness, rel_rmse, dst, corr, corr_d2, partial);
     }
     T3D_LAUNCH_CHECK();
     ctx->launches += 2 * n;
@@ -685,6 +707,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const float*
   res->iterations = hst->iterations;
   res->converged = hst->converged;
   res->correspondences = (int64_t)hst->acc[28];
+  if (skipped_h) *skipped_h = hst->skipped;
   return T3D_OK;
 }
 
@@ -723,6 +746,22 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
   if (n_src == 0 || n_tgt == 0) return T3D_OK;
   T3D_REQUIRE(src && tgt && tgt_nrm, "t3d_icp_point_to_plane: null clouds");
   cudaStream_t st = as_stream(stream);
-  return icp_fused(ctx, src, n_src, tgt, tgt_nrm, n_tgt, max_corr_dist, res->T, max_iter, rel_fitness,
-                   rel_rmse, res, st);
+  return icp_fused(ctx, src, n_src, nullptr, tgt, tgt_nrm, n_tgt, nullptr, 0, max_corr_dist, res->T, max_iter,
+                   rel_fitness, rel_rmse, res, nullptr, st);
+}
+
+extern "C" int t3d_icp_point_to_plane_dev(t3d_ctx* ctx, const float* src, int64_t src_capacity,
+                                          const int64_t* n_src_dev, const float* tgt, const float* tgt_nrm,
+                                          int64_t tgt_capacity, const int64_t* n_tgt_dev, int min_points,
+                                          double max_corr_dist, const double* T0_h, int max_iter,
+                                          double rel_fitness, double rel_rmse, t3d_icp_result* res,
+                                          int* skipped_h, t3d_stream stream) {
+  T3D_REQUIRE(ctx && res && src && tgt && tgt_nrm && n_src_dev && n_tgt_dev && src_capacity > 0 && tgt_capacity > 0,
+              "t3d_icp_point_to_plane_dev: null argument");
+  T3D_REQUIRE(max_corr_dist > 0.0 && max_iter >= 0, "t3d_icp_point_to_plane_dev: bad parameters");
+  memset(res, 0, sizeof(*res));
+  for (int i = 0; i < 16; ++i) res->T[i] = T0_h ? T0_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);
+  return icp_fused(ctx, src, src_capacity, reinterpret_cast<const long long*>(n_src_dev), tgt, tgt_nrm,
+                   tgt_capacity, reinterpret_cast<const long long*>(n_tgt_dev), min_points, max_corr_dist, res->T,
+                   max_iter, rel_fitness, rel_rmse, res, skipped_h, as_stream(stream));
 }

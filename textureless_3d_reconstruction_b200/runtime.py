@@ -246,6 +246,26 @@ class Context:
         return IcpOutput(np.array(res.T[:], np.float64).reshape(4, 4), res.fitness, res.inlier_rmse,
                          res.iterations, bool(res.converged), int(res.correspondences))
 
+    def icp_point_to_plane_dev(self, src, n_src_dev, tgt, tgt_nrm, n_tgt_dev, max_corr_dist, init=None, max_iter=30,
+                               relative_fitness=1e-6, relative_rmse=1e-6, min_points=0):
+        """Same registration with the cloud sizes in device memory (int64[1] tensors): src / tgt are
+        capacity-sized buffers.  Returns (IcpOutput, skipped) — skipped=True when a cloud had fewer
+        than min_points points (no registration, transformation = init)."""
+        torch = _torch()
+        for t in (src, tgt, tgt_nrm):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        assert n_src_dev.dtype == torch.int64 and n_tgt_dev.dtype == torch.int64
+        T0 = None if init is None else np.ascontiguousarray(init, np.float64).reshape(16)
+        res = IcpResult()
+        skipped = C.c_int(0)
+        check(self.lib.t3d_icp_point_to_plane_dev(
+            self.handle, _ptr(src), src.shape[0], _ptr(n_src_dev), _ptr(tgt), _ptr(tgt_nrm), tgt.shape[0],
+            _ptr(n_tgt_dev), int(min_points), float(max_corr_dist), _np_ptr(T0), int(max_iter),
+            float(relative_fitness), float(relative_rmse), C.byref(res), C.byref(skipped), _stream()))
+        out = IcpOutput(np.array(res.T[:], np.float64).reshape(4, 4), res.fitness, res.inlier_rmse,
+                        res.iterations, bool(res.converged), int(res.correspondences))
+        return out, bool(skipped.value)
+
     def icp_linearize(self, src, tgt, tgt_nrm, max_corr_dist, T):
         """One linearisation: returns (acc27, sum_d2, count) as host values."""
         Th = np.ascontiguousarray(T, np.float64).reshape(16)
@@ -564,6 +584,33 @@ class TSDFVolume:
                 return xyz[:cnt], (nrm[:cnt] if nrm is not None else None), (rgb[:cnt] if rgb is not None else None)
             cap = cnt
 
+
+    def extract_points_view_async(self, K, T_cw, H, W, depth_max, weight_threshold, buffers, with_normals=True,
+                                  with_colors=False):
+        """K6 over the blocks visible from (K, T_cw) with NO host synchronisation: fills the capacity-sized
+        tensors of `buffers` (created/grown by ensure_view_buffers) and leaves the point count in
+        buffers["n"] (int64[1], device).  The caller checks buffers["n"] <= capacity when it next syncs."""
+        arr = (FrameView * 1)()
+        arr[0].depth = None
+        arr[0].bgr = None
+        arr[0].K[:] = np.asarray(K, np.float32).reshape(4).tolist()
+        arr[0].T_cw[:] = np.asarray(T_cw, np.float64)[:3, :4].astype(np.float32).reshape(12).tolist()
+        check(self.lib.t3d_tsdf_extract_points_view(
+            self.handle, arr, int(H), int(W), float(depth_max), float(weight_threshold), _ptr(buffers["xyz"]),
+            _ptr(buffers["nrm"]) if with_normals else None, _ptr(buffers["rgb"]) if with_colors else None,
+            buffers["xyz"].shape[0], _ptr(buffers["n"]), None, _stream()))
+        return buffers
+
+    def ensure_view_buffers(self, buffers, cap):
+        torch = _torch()
+        dev = self.ctx.device
+        if buffers.get("xyz") is None or buffers["xyz"].shape[0] < cap:
+            buffers["xyz"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            buffers["nrm"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            buffers["rgb"] = torch.empty((cap, 3), dtype=torch.uint8, device=dev)
+            buffers["n"] = torch.zeros(1, dtype=torch.int64, device=dev)
+            buffers["cap"] = cap
+        return buffers
 
     def extract_points_view(self, K, T_cw, H, W, depth_max=5.0, weight_threshold=1.0, with_normals=True,
                             with_colors=False, buffers=None):

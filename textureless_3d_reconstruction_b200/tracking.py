@@ -74,6 +74,7 @@ class FrameToModelTracker:
         return t0
 
     def _source_cloud(self, depth):
+        """K1 in the camera frame into a reusable buffer; the point count stays on the device."""
         torch = __import__("torch")
         s = self.icp_subsample
         cap = (-(-self.H // s)) * (-(-self.W // s))
@@ -83,24 +84,34 @@ class FrameToModelTracker:
         xyz, n = self._src
         self.ctx.backproject(depth, None, fx=self.K[0], fy=self.K[1], cx=self.K[2], cy=self.K[3], subsample=s,
                              min_depth=self.min_depth, max_depth=self.depth_max, pose=None, out_xyz=xyz, out_n=n)
-        return xyz[: int(n.item())]
+        return xyz, n
 
     def track(self, depth, guess):
         """ICP of one frame against the model seen from `guess` (world->camera 4x4).
-        Returns (T_cw, IcpOutput | None)."""
+        Returns (T_cw, IcpOutput | None).  The model surface (K6), the frame's cloud (K1) and the whole
+        registration (K8) are enqueued back to back; cloud sizes stay in device memory and the host
+        synchronises once, on the registration result."""
         import time
-        t0 = time.perf_counter()
-        tgt, tgt_n, _, nsel = self.volume.extract_points_view(self.K, guess, self.H, self.W, self.depth_max,
-                                                              self.weight_threshold, buffers=self._tgt)
-        self.last_target = (int(tgt.shape[0]), nsel)
-        t0 = self._stage("extract_view", t0)
-        src = self._source_cloud(depth)
-        t0 = self._stage("backproject", t0)
-        if tgt.shape[0] < self.min_points or src.shape[0] < self.min_points:
+        vol = self.volume
+        while True:
+            t0 = time.perf_counter()
+            vol.ensure_view_buffers(self._tgt, int(self._tgt.get("cap", 1 << 18)))
+            vol.extract_points_view_async(self.K, guess, self.H, self.W, self.depth_max, self.weight_threshold, self._tgt)
+            t0 = self._stage("extract_view", t0)
+            src, n_src = self._source_cloud(depth)
+            t0 = self._stage("backproject", t0)
+            res, skipped = self.ctx.icp_point_to_plane_dev(src, n_src, self._tgt["xyz"], self._tgt["nrm"], self._tgt["n"],
+                                                           self.icp_max_corr, init=np.linalg.inv(guess),
+                                                           max_iter=self.icp_max_iter, min_points=self.min_points)
+            self._stage("icp", t0)
+            n_tgt = int(self._tgt["n"].item())          # stream is idle here: the ICP result was just read
+            if n_tgt <= self._tgt["cap"]:
+                break
+            self._tgt["cap"] = int(n_tgt * 1.25) + 1024   # surface grew past the buffer: enlarge, redo this frame
+            self._tgt["xyz"] = None
+        self.last_target = (n_tgt, None)
+        if skipped:
             return guess, None
-        res = self.ctx.icp_point_to_plane(src, tgt, tgt_n, self.icp_max_corr, init=np.linalg.inv(guess),
-                                          max_iter=self.icp_max_iter)
-        self._stage("icp", t0)
         return np.linalg.inv(res.transformation), res
 
     def add_frame(self, depth, bgr, init_pose=None, known_pose=None):
