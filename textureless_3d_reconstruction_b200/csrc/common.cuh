@@ -99,6 +99,12 @@ struct t3d_ctx {
   // pinned host staging for small synchronous results
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // cached CUDA graphs of launch-bound inner loops (key = every baked-in pointer/scalar)
+  struct CachedGraph {
+    std::string key;
+    cudaGraphExec_t exec = nullptr;
+  };
+  std::vector<CachedGraph> graphs;
 };
 
 // host-side phase timing, printed to stderr when T3D_TRACE is set (debug aid)

@@ -67,6 +67,8 @@ extern "C" void t3d_destroy(t3d_ctx* ctx) {
     cudaFree(t.yf);
   }
   ctx->scan_state.release();
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (DevBuf& b : ctx->scratch) b.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;

@@ -655,47 +655,94 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   int* corr = ctx->scratch[3].as<int>();
   double* corr_d2 = ctx->scratch[4].as<double>();
 
-  T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
-  T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
-  T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
-  T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
-  const int bgrid = (int)((n_tgt + 255) / 256 < (long long)ctx->num_sms * 8 ? (n_tgt + 255) / 256 : (long long)ctx->num_sms * 8);
-  hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
-  T3D_LAUNCH_CHECK();
-  hg_alloc_kernel<<<(int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368), 256, 0, st>>>(g);
-  T3D_LAUNCH_CHECK();
-  hg_dilate_kernel<<<(int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368), 256, 0, st>>>(g);
-  T3D_LAUNCH_CHECK();
-  hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
-  T3D_LAUNCH_CHECK();
-  ctx->launches += 4;
-
   IcpState* hst = reinterpret_cast<IcpState*>(reinterpret_cast<char*>(ctx->pinned) + 2048);
   unsigned* hflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + 1024);
   memset(hst, 0, sizeof(IcpState));
   for (int i = 0; i < 16; ++i) hst->T[i] = T0[i];
-  T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
   const double r2 = max_corr * max_corr;
-  // rounds needed: at most max_iter + 1.  Enqueue speculatively (finished rounds are no-op
-  // launches), read the state back, continue only if the registration is still running.
-  int enqueued = 0;
-  int chunk = 6;
-  while (true) {
-    int n = max_iter + 1 - enqueued;
-    if (n > chunk) n = chunk;
-    for (int r = 0; r < n; ++r) {
+  const int bgrid = (int)((n_tgt + 255) / 256 < (long long)ctx->num_sms * 8 ? (n_tgt + 255) / 256 : (long long)ctx->num_sms * 8);
+  const int hgrid = (int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368);
+
+  // grid build + initial state + `rounds` linearisations + result read-back, all on stream st
+  auto enqueue_all = [&](int rounds, bool with_build) -> int {
+    if (with_build) {
+      T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
+      T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
+      T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
+      T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
+      hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
+      hg_alloc_kernel<<<hgrid, 256, 0, st>>>(g);
+      hg_dilate_kernel<<<hgrid, 256, 0, st>>>(g);
+      hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
+      T3D_LAUNCH_CHECK();
+      T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
+    }
+    for (int r = 0; r < rounds; ++r) {
       icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2);
       icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, min_points, max_iter,
                                                         rel_fitness, rel_rmse, dst, corr, corr_d2, partial);
     }
     T3D_LAUNCH_CHECK();
-    ctx->launches += 2 * n;
-    enqueued += n;
     T3D_CUDA(cudaMemcpyAsync(hst, dst, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
     T3D_CUDA(cudaMemcpyAsync(hflag, g.cursor, 8, cudaMemcpyDeviceToHost, st));
+    return T3D_OK;
+  };
+
+  // rounds needed: at most max_iter + 1.  Enqueue speculatively (finished rounds are no-op
+  // launches), read the state back, continue only if the registration is still running.
+  // On a capturable stream the first chunk (build + 6 rounds + read-back, ~24 operations that
+  // are each a few microseconds long) is one cached CUDA graph launch.
+  int enqueued = 0;
+  const int first = max_iter + 1 < 6 ? max_iter + 1 : 6;
+  static int use_graph = -1;
+  if (use_graph < 0) { const char* e = getenv("T3D_ICP_GRAPH"); use_graph = (e && atoi(e) == 0) ? 0 : 1; }
+  bool launched = false;
+  if (use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) {
+    char key[512];
+    snprintf(key, sizeof(key), "icp|%p|%p|%p|%p|%p|%lld|%lld|%.17g|%d|%d|%.17g|%.17g|%p|%p|%p|%p|%p|%p|%d", (const void*)src,
+             (const void*)n_src_dev, (const void*)tgt, (const void*)tgt_nrm, (const void*)n_tgt_dev, (long long)n_src,
+             (long long)n_tgt, max_corr, max_iter, min_points, rel_fitness, rel_rmse, ctx->scratch[0].p,
+             ctx->scratch[1].p, ctx->scratch[2].p, ctx->scratch[3].p, ctx->scratch[4].p, ctx->scratch[6].p, first);
+    cudaGraphExec_t exec = nullptr;
+    for (auto& cg : ctx->graphs)
+      if (cg.key == key) exec = cg.exec;
+    if (!exec) {
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int erc = enqueue_all(first, true);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (erc == T3D_OK && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          if (ctx->graphs.size() >= 8) {  // bounded cache
+            for (auto& cg : ctx->graphs) cudaGraphExecDestroy(cg.exec);
+            ctx->graphs.clear();
+          }
+          ctx->graphs.push_back({key, exec});
+        } else {
+          exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();  // a failed capture must not poison later calls
+      }
+    }
+    if (exec) {
+      T3D_CUDA(cudaGraphLaunch(exec, st));
+      launched = true;
+    }
+  }
+  if (!launched) {
+    if ((rc = enqueue_all(first, true)) != T3D_OK) return rc;
+  }
+  ctx->launches += 4 + 2 * first;
+  enqueued = first;
+  T3D_CUDA(cudaStreamSynchronize(st));
+  while (!hst->done && enqueued < max_iter + 1) {
+    int n = max_iter + 1 - enqueued;
+    if (n > 8) n = 8;
+    if ((rc = enqueue_all(n, false)) != T3D_OK) return rc;
+    ctx->launches += 2 * n;
+    enqueued += n;
     T3D_CUDA(cudaStreamSynchronize(st));
-    if (hst->done || enqueued >= max_iter + 1) break;
-    chunk = 8;
   }
   if (hflag[1]) {
     t3d_set_error("icp: target coordinates exceed +-2^19 * max_corr_dist");

@@ -58,11 +58,18 @@ class FrameToModelTracker:
         self.icp_log = []        # IcpOutput | None per frame
         self._tgt = {}           # reusable target buffers
         self._src = None
+        # a private (capturable) stream: the registration's launch-bound inner loop runs as a cached
+        # CUDA graph, which the legacy default stream cannot capture
+        self.stream = __import__("torch").cuda.Stream(device=self.ctx.device)
         self.stage_ms = None     # set to {} to collect synchronised per-stage wall times (profiling aid)
 
     def reset(self):
         """Forget the model and the trajectory (buffers are kept)."""
-        self.volume.reset()
+        torch = __import__("torch")
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.volume.reset()
+        torch.cuda.current_stream().wait_stream(self.stream)
         self.poses, self.icp_log = [], []
 
     def _stage(self, name, t0):
@@ -117,19 +124,27 @@ class FrameToModelTracker:
     def add_frame(self, depth, bgr, init_pose=None, known_pose=None):
         """Track (unless known_pose is given) and fuse one frame.  depth (H,W) f32 and
         bgr (H,W,3) u8 are CUDA tensors.  Returns the frame's world->camera 4x4."""
-        res = None
-        if known_pose is not None:
-            T = as4x4(known_pose)
-        elif not self.poses:
-            T = as4x4(init_pose) if init_pose is not None else np.eye(4)
-        else:
-            guess = as4x4(init_pose) if init_pose is not None else predict_pose(
-                self.poses[-1], self.poses[-2] if len(self.poses) > 1 else None, self.motion_model)
-            T, res = self.track(depth, guess)
         import time
-        t0 = time.perf_counter()
-        self.volume.integrate(depth, bgr, self.K, T, depth_scale=1.0, depth_max=self.depth_max)
-        self._stage("integrate", t0)
+        torch = __import__("torch")
+        caller = torch.cuda.current_stream()
+        self.stream.wait_stream(caller)                 # the frame was produced on the caller's stream
+        depth.record_stream(self.stream)
+        if bgr is not None:
+            bgr.record_stream(self.stream)
+        res = None
+        with torch.cuda.stream(self.stream):
+            if known_pose is not None:
+                T = as4x4(known_pose)
+            elif not self.poses:
+                T = as4x4(init_pose) if init_pose is not None else np.eye(4)
+            else:
+                guess = as4x4(init_pose) if init_pose is not None else predict_pose(
+                    self.poses[-1], self.poses[-2] if len(self.poses) > 1 else None, self.motion_model)
+                T, res = self.track(depth, guess)
+            t0 = time.perf_counter()
+            self.volume.integrate(depth, bgr, self.K, T, depth_scale=1.0, depth_max=self.depth_max)
+            self._stage("integrate", t0)
+        caller.wait_stream(self.stream)                 # later work of the caller sees the updated model
         self.poses.append(T)
         self.icp_log.append(res)
         return T
