@@ -1,0 +1,106 @@
+"""The two drop-in CLIs end to end on the GPU (BASELINE configs[0] and [2] at reduced size):
+folders of RGB + depth files in the reference's formats -> main() -> .ply, checked against the
+oracle pipeline (reference NumPy back-projection restatement + R2 + R3) / the synthetic ground truth."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from textureless_3d_reconstruction_b200 import synthetic as S
+
+
+def read_o3d_ply(path):
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    assert lines[0] == "ply" and lines[1] == "format binary_little_endian 1.0"
+    n = int(next(l for l in lines if l.startswith("element vertex")).split()[-1])
+    props = [l.split()[1:] for l in lines if l.startswith("property")]
+    assert [p[1] for p in props] == ["x", "y", "z", "red", "green", "blue"] and props[0][0] == "double"
+    rec = np.frombuffer(body, dtype=np.dtype([("p", "<f8", 3), ("c", "u1", 3)]), count=n)
+    return rec["p"].copy(), rec["c"].copy()
+
+
+def write_dataset(tmp_path, scene, n, H, W, K):
+    import cv2
+    rgb_dir, depth_dir = tmp_path / "rgb", tmp_path / "depth"
+    rgb_dir.mkdir()
+    depth_dir.mkdir()
+    frames, poses = [], []
+    for i in range(n):
+        d, c, T = S.synth_frame(scene, i, H, W, *K, noise_sigma=0.002 if scene == 0 else 0.0)
+        cv2.imwrite(str(rgb_dir / f"frame_{i:04d}.png"), c)                 # lossless BGR
+        np.save(depth_dir / f"frame_{i:04d}_depth.npy", d)                  # dp:908 format, found first (d2r:105)
+        P = np.eye(4)
+        P[:3, :4] = T
+        frames.append((d, c))
+        poses.append(P)
+    np.save(tmp_path / "poses.npy", np.stack(poses))
+    return rgb_dir, depth_dir, frames, poses
+
+
+def test_d2r_cli_matches_oracle_pipeline(ctx, oracle, tmp_path, capsys):
+    from oracle import ref_numpy
+    from textureless_3d_reconstruction_b200 import depth_to_reconstruction as d2r
+    H, W, n = 480, 270, 6          # scene S1 carries a 64-px invalid border band
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    rgb_dir, depth_dir, frames, poses = write_dataset(tmp_path, 1, n, H, W, K)
+    out = tmp_path / "out" / "reconstruction.ply"
+    d2r.main(["--rgb-folder", str(rgb_dir), "--depth-folder", str(depth_dir), "--output", str(out), "--fx", str(K[0]),
+              "--fy", str(K[1]), "--cx", str(K[2]), "--cy", str(K[3]), "--voxel-size", "0.02", "--subsample", "2",
+              "--no-vis", "--poses", str(tmp_path / "poses.npy")])
+    text = capsys.readouterr().out
+    assert f"Loaded {n} image-depth pairs" in text and "Camera 0:" in text and "Final reconstruction:" in text
+    assert f"Saved to {out}" in text
+    gp, gc = read_o3d_ply(out)
+    # oracle pipeline: reference arithmetic for K1 (d2r:328-384), R2, R3 (d2r:405-418)
+    clouds = [ref_numpy.d2r_depth_to_pointcloud(d, c, *K, pose=(P[:3, :3], P[:3, 3:4]), scale=1.0, subsample=2)
+              for (d, c), P in zip(frames, poses)]
+    pts = np.vstack([p for p, _ in clouds])
+    cols = np.vstack([c for _, c in clouds])
+    o = oracle.voxel_downsample(pts.astype(np.float64), cols, 0.02)
+    order = np.lexsort(o["idx"].T[::-1])
+    op, oc = o["points"][order], o["colors_u8"][order]
+    keep, mean, (mu, sigma, thr) = oracle.statistical_outlier(op, 20, 2.0)
+    boundary = int((np.abs(mean - thr) < 1e-9 * thr).sum())
+    op, oc = op[keep], oc[keep]
+    assert abs(len(gp) - len(op)) <= boundary and len(gp) > 2000
+    if len(gp) == len(op):
+        assert np.allclose(gp, op, rtol=1e-12, atol=0)                      # f64 voxel means: exact sums
+        assert np.abs(gc.astype(int) - oc.astype(int)).max() <= 1
+    print(f"d2r cli: {len(gp)} points (oracle {len(op)}, {boundary} threshold-boundary points)")
+
+
+def test_der_cli_tracks_and_writes_ply(ctx, tmp_path, capsys):
+    from textureless_3d_reconstruction_b200 import depth_enhanced_reconstruction as der
+    H, W, n = 480, 270, 8
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    rgb_dir, depth_dir, frames, poses = write_dataset(tmp_path, 0, n, H, W, K)
+    Kmat = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]])
+    rec = der.DepthEnhancedReconstruction(K=Kmat, block_capacity=60000, icp_subsample=2)
+    assert rec.load_images(str(rgb_dir)) == n and rec.load_depths(str(depth_dir)) == n
+    res = rec.reconstruct(output_dir=str(tmp_path / "o"), init_poses=None)
+    assert res is not None
+    pts, cols, cam = res
+    text = capsys.readouterr().out
+    assert "RECONSTRUCTION COMPLETE" in text and f"Saved {len(pts)} points to" in text        # der:1311
+    gp, gc = read_o3d_ply(tmp_path / "o" / "reconstruction.ply")                             # der:1247
+    assert len(gp) == len(pts) > 10000 and np.allclose(gp, pts.astype(np.float64))
+    # frame 0 defines the world frame (identity); later poses follow the ground-truth motion relative to it
+    G0 = poses[0]
+    for i in (3, n - 1):
+        rel_gt = poses[i] @ np.linalg.inv(G0)
+        P = np.eye(4)
+        P[:3, :3], P[:3, 3:4] = cam[i]
+        E = P @ np.linalg.inv(rel_gt)
+        assert np.linalg.norm(E[:3, 3]) < 0.03, (i, E[:3, 3])
+    # CLI: fewer than two images -> exit(1) like the reference (der:1452-1454)
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(SystemExit) as e:
+        der.main(["--input", str(empty), "--output", str(tmp_path / "o2")])
+    assert e.value.code == 1
