@@ -135,6 +135,57 @@ def main():
                  valid_points=nvalid, sampled_pixels=P * NF)
             del o_xyz, o_rgb
 
+    if "CFG1" in only:
+        # BASELINE configs[0]: depth_to_reconstruction's dense path on 30 x 1080x1920 frames (scene S1, given
+        # poses, subsample 2 = CLI default, voxel 0.005, outlier removal) from HBM-resident frames to a .ply
+        from oracle import ref_numpy
+        from textureless_3d_reconstruction_b200 import depth_to_reconstruction as d2r
+        from textureless_3d_reconstruction_b200.runtime import write_ply
+        n1 = 30
+        d1 = torch.empty((n1, H, W), dtype=torch.float32, device=dev)
+        c1 = torch.empty((n1, H, W, 3), dtype=torch.uint8, device=dev)
+        p1 = []
+        for i in range(n1):
+            _, _, T = ctx.synth_frame(1, i, H, W, *K4, seed=1234, depth=d1[i], bgr=c1[i])
+            p1.append((T[:, :3].copy(), T[:, 3:4].copy()))
+        dense = d2r.DenseReconstructor(d2r.ReconstructionConfig())
+        fr1 = ctx.make_backproject_frames([d1[i] for i in range(n1)], [c1[i] for i in range(n1)], p1)
+        out = {}
+
+        def cfg1(i):
+            xyz, rgb, offs = ctx.backproject_batch(fr1, n1, H, W, fx=K4[0], fy=K4[1], cx=K4[2], cy=K4[3], subsample=2,
+                                                   min_depth=0.1, max_depth=50.0)
+            n = int(offs[-1].item())
+            pts, cols = dense.merge_pointclouds_device(xyz[:n], rgb[:n], 0.005)
+            out["r"] = (n, pts.cpu().numpy(), cols.cpu().numpy())
+        ms = gpu_time(cfg1, 3, warm=1)
+        n_in, pts_h, cols_h = out["r"]
+        t0 = time.perf_counter()
+        write_ply("/tmp/_t3d_cfg1.ply", pts_h, cols_h, layout=0)
+        ply_s = time.perf_counter() - t0
+        # CPU: the reference's NumPy arithmetic for K1 + the oracle for the two Open3D calls
+        hd, hc = d1.cpu().numpy(), c1.cpu().numpy()
+        t0 = time.perf_counter()
+        clouds = [ref_numpy.d2r_depth_to_pointcloud(hd[i], hc[i], *K4, pose=p1[i], scale=1.0, subsample=2) for i in range(n1)]
+        t_k1 = time.perf_counter() - t0
+        P = np.vstack([a for a, _ in clouds]).astype(np.float64)
+        Cc = np.vstack([b for _, b in clouds])
+        t0 = time.perf_counter()
+        o = capi.voxel_downsample(P, Cc, 0.005)
+        t_k2 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        keep, _, _ = capi.statistical_outlier(o["points"], 20, 2.0)
+        t_k3 = time.perf_counter() - t0
+        print(json.dumps({"kernel": "CFG1 d2r dense path: 30 frames 1080x1920, s=2, voxel 5 mm, SOR (HBM -> host arrays)",
+                          "frames": n1, "ms": ms, "frames_per_s": n1 / (ms * 1e-3), "points_in": n_in,
+                          "points_out": int(len(pts_h)), "ply_write_s": ply_s,
+                          "cpu_baseline": {"seconds": t_k1 + t_k2 + t_k3, "frames_per_s": n1 / (t_k1 + t_k2 + t_k3),
+                                           "k1_numpy_reference_restatement_s": t_k1, "k2_oracle_serial_s": t_k2,
+                                           "k3_oracle_openmp_s": t_k3, "cores": cores, "points_out": int(keep.sum())},
+                          "same_point_count_as_cpu": bool(abs(int(keep.sum()) - len(pts_h)) <= 2)}), flush=True)
+        del d1, c1
+        return
+
     # ------------------------------------------------------------------ fused cloud for K2/K3/K7
     NC = 4 if args.quick else 16
     clouds, cols = [], []
