@@ -308,6 +308,21 @@ int t3d_tsdf_extract_points_view(t3d_tsdf* v, const t3d_frame_view* view_h, int 
                                  int64_t capacity, int64_t* out_n,
                                  int64_t* out_blocks_h, t3d_stream stream);
 
+/* K10 — triangle-mesh extraction (north_star "surface/point extraction to .ply", SURVEY 8f
+ * rank 3; no reference code — semantics of Open3D VoxelBlockGrid.extract_triangle_mesh, R6m in
+ * the oracle).  A cube (voxel + its 7 upper neighbours) is valid iff all 8 voxels have
+ * W >= weight_threshold; case bit i = tsdf(corner i) < 0; every sign-changing edge of a valid
+ * cube carries one vertex with R6's position / normal / colour; triangles from the table in
+ * csrc/mc_tables.cuh, wound so that their normals follow the TSDF gradient.
+ * xyz, nrm: vertex_capacity*3 f32; rgb: vertex_capacity*3 u8 (nrm, rgb nullable);
+ * tri: triangle_capacity*3 int32 vertex indices.  out_counts (device int64[2]) = {vertices,
+ * triangles}; a count above its capacity means that output was truncated.  Pass both capacities
+ * as 0 to count only.  Vertex / triangle order is unspecified.  Synchronous (block count). */
+int t3d_tsdf_extract_mesh(t3d_tsdf* v, float weight_threshold, float* xyz, float* nrm,
+                          uint8_t* rgb, int64_t vertex_capacity, int32_t* tri,
+                          int64_t triangle_capacity, int64_t* out_counts,
+                          t3d_stream stream);
+
 /* ------------------------------------------------------------------------- */
 /* K7 — normal estimation (north_star; Open3D estimate_normals KNN, R7).      */
 /* ------------------------------------------------------------------------- */
@@ -380,6 +395,13 @@ int t3d_nearest_neighbor(t3d_ctx* ctx, const float* query, int64_t n_q,
 int t3d_write_ply_h(const char* path, const void* xyz_h, int xyz_is_f64,
                     const uint8_t* rgb_h, const void* nrm_h, int64_t n,
                     int layout);
+
+/* Triangle mesh as Open3D's write_triangle_mesh writes it: binary little-endian, vertex
+ * `double x y z [nx ny nz]` + `uchar red green blue`, then `element face` with
+ * `property list uchar uint vertex_indices`.  xyz_h, nrm_h: nv*3 f32; tri_h: nt*3 int32. */
+int t3d_write_ply_mesh_h(const char* path, const float* xyz_h, const float* nrm_h,
+                         const uint8_t* rgb_h, int64_t nv, const int32_t* tri_h,
+                         int64_t nt);
 
 /* ------------------------------------------------------------------------- */
 /* Formats either side of the path.                              */

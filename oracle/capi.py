@@ -18,7 +18,8 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     src = _DIR / "t3d_oracle.c"
-    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+    newest = max(src.stat().st_mtime, (_DIR / "mc_tables.h").stat().st_mtime)
+    if force or not _SO.exists() or _SO.stat().st_mtime < newest:
         base = ["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fno-fast-math", "-fPIC", "-shared",
                 "-fvisibility=hidden", "-o", str(_SO), str(src), "-lm"]
         r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], capture_output=True, text=True)
@@ -213,6 +214,13 @@ class TSDFVolume:
         lib().o_tsdf_export(self._h, _p(keys), _p(tsdf), _p(w), _p(rgb))
         return keys, tsdf, w, rgb
 
+    def import_blocks(self, keys, tsdf, weight, rgb=None):
+        keys = np.ascontiguousarray(keys, np.int32)
+        tsdf = np.ascontiguousarray(tsdf, np.float32)
+        weight = np.ascontiguousarray(weight, np.float32)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+        lib().o_tsdf_import(self._h, _p(keys), _p(tsdf), _p(weight), _p(rgb), C.c_int64(len(keys)))
+
     def extract_points(self, weight_threshold=3.0, view=None):
         """view = (K(fx,fy,cx,cy), T_cw 3x4|4x4, H, W, depth_max): only blocks visible from that
         camera (the frame-to-model tracker's target, see o_block_in_view)."""
@@ -238,3 +246,18 @@ class TSDFVolume:
             if n <= cap:
                 return xyz[:n].copy(), nrm[:n].copy(), rgb[:n].copy()
             cap = n
+
+    def extract_mesh(self, weight_threshold=3.0):
+        """R6m: (vertices f32 Vx3, normals f32 Vx3, colours u8 Vx3, triangles i32 Tx3)."""
+        vcap, tcap = max(self.num_blocks * 96, 1024), max(self.num_blocks * 192, 1024)
+        while True:
+            xyz = np.empty((vcap, 3), np.float32)
+            nrm = np.empty((vcap, 3), np.float32)
+            rgb = np.empty((vcap, 3), np.uint8)
+            tri = np.empty((tcap, 3), np.int32)
+            n = np.zeros(2, np.int64)
+            lib().o_tsdf_extract_mesh(self._h, C.c_float(weight_threshold), _p(xyz), _p(nrm), _p(rgb), C.c_int64(vcap),
+                                      _p(tri), C.c_int64(tcap), _p(n))
+            if n[0] <= vcap and n[1] <= tcap:
+                return xyz[:n[0]].copy(), nrm[:n[0]].copy(), rgb[:n[0]].copy(), tri[:n[1]].copy()
+            vcap, tcap = int(n[0]), int(n[1])

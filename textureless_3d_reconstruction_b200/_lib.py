@@ -101,6 +101,8 @@ _SIGS = {
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    "t3d_tsdf_extract_mesh": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _I64, _VP, _VP]),
+    "t3d_write_ply_mesh_h": (_I, [C.c_char_p, _VP, _VP, _VP, _I64, _VP, _I64]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),
     "t3d_icp_point_to_plane": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _I, _D, _D, C.POINTER(IcpResult), _VP]),
     "t3d_icp_point_to_plane_dev": (_I, [_VP, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I, _D, _VP, _I, _D, _D,

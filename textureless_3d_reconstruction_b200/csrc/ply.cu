@@ -152,3 +152,51 @@ extern "C" int t3d_write_ply_h(const char* path, const void* xyz_h, int xyz_is_f
   }
   return T3D_OK;
 }
+
+extern "C" int t3d_write_ply_mesh_h(const char* path, const float* xyz_h, const float* nrm_h,
+                                    const uint8_t* rgb_h, int64_t nv, const int32_t* tri_h, int64_t nt) {
+  T3D_REQUIRE(path && nv >= 0 && nt >= 0 && (nv == 0 || xyz_h) && (nt == 0 || tri_h),
+              "t3d_write_ply_mesh_h: null argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    t3d_set_error("t3d_write_ply_mesh_h: cannot open %s", path);
+    return T3D_E_IO;
+  }
+  bool ok = fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\n"
+                       "element vertex %lld\nproperty double x\nproperty double y\nproperty double z\n",
+                    (long long)nv) > 0;
+  if (nrm_h) ok = ok && fprintf(f, "property double nx\nproperty double ny\nproperty double nz\n") > 0;
+  if (rgb_h) ok = ok && fprintf(f, "property uchar red\nproperty uchar green\nproperty uchar blue\n") > 0;
+  ok = ok && fprintf(f, "element face %lld\nproperty list uchar uint vertex_indices\nend_header\n",
+                     (long long)nt) > 0;
+  std::vector<char> buf;
+  buf.reserve(1 << 22);
+  auto flush = [&]() {
+    if (!buf.empty()) ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    buf.clear();
+  };
+  for (int64_t i = 0; i < nv; ++i) {
+    double rec[6];
+    int k = 0;
+    for (int c = 0; c < 3; ++c) rec[k++] = (double)xyz_h[i * 3 + c];
+    if (nrm_h) for (int c = 0; c < 3; ++c) rec[k++] = (double)nrm_h[i * 3 + c];
+    const char* rb = reinterpret_cast<const char*>(rec);
+    buf.insert(buf.end(), rb, rb + k * 8);
+    if (rgb_h) buf.insert(buf.end(), rgb_h + i * 3, rgb_h + i * 3 + 3);
+    if (buf.size() > (1 << 22) - 256) flush();
+  }
+  for (int64_t i = 0; i < nt; ++i) {
+    char rec[13];
+    rec[0] = 3;
+    memcpy(rec + 1, tri_h + i * 3, 12);
+    buf.insert(buf.end(), rec, rec + 13);
+    if (buf.size() > (1 << 22) - 256) flush();
+  }
+  flush();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) {
+    t3d_set_error("t3d_write_ply_mesh_h: write to %s failed", path);
+    return T3D_E_IO;
+  }
+  return T3D_OK;
+}

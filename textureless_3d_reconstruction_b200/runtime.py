@@ -7,11 +7,12 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
+from pathlib import Path
 
 import numpy as np
 
 from . import _lib
-from ._lib import BackprojectFrame, BackprojectParams, FrameView, IcpResult, TsdfParams, check
+from ._lib import BackprojectFrame, BackprojectParams, FrameView, IcpResult, T3DError, TsdfParams, check
 
 _contexts: dict[int, "Context"] = {}
 
@@ -585,6 +586,28 @@ class TSDFVolume:
             cap = cnt
 
 
+    def extract_mesh(self, weight_threshold=3.0, with_normals=True, with_colors=True):
+        """K10: marching-cubes triangle mesh of the fused surface (Open3D extract_triangle_mesh
+        semantics).  Returns (vertices f32 Vx3, normals f32 Vx3|None, colours u8 Vx3|None,
+        triangles i32 Tx3) on the device.  Two passes: count, then fill exactly-sized buffers."""
+        torch = _torch()
+        dev = self.ctx.device
+        n = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(self.lib.t3d_tsdf_extract_mesh(self.handle, float(weight_threshold), None, None, None, 0, None, 0,
+                                             _ptr(n), _stream()))
+        nv, nt = (int(x) for x in n.tolist())
+        if nv >= 2**31 - 1 or nt >= 2**31 - 1:
+            raise T3DError(-1, f"mesh too large for 32-bit indices: {nv} vertices, {nt} triangles")
+        xyz = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        nrm = torch.empty((nv, 3), dtype=torch.float32, device=dev) if with_normals else None
+        rgb = torch.empty((nv, 3), dtype=torch.uint8, device=dev) if with_colors else None
+        tri = torch.empty((nt, 3), dtype=torch.int32, device=dev)
+        if nv == 0:
+            return xyz, nrm, rgb, tri
+        check(self.lib.t3d_tsdf_extract_mesh(self.handle, float(weight_threshold), _ptr(xyz), _ptr(nrm), _ptr(rgb),
+                                             nv, _ptr(tri), nt, _ptr(n), _stream()))
+        return xyz, nrm, rgb, tri
+
     def extract_points_view_async(self, K, T_cw, H, W, depth_max, weight_threshold, buffers, with_normals=True,
                                   with_colors=False):
         """K6 over the blocks visible from (K, T_cw) with NO host synchronisation: fills the capacity-sized
@@ -659,3 +682,21 @@ def write_ply(path, points, colors=None, normals=None, layout=_lib.PLY_O3D_BINAR
     nr = None if normals is None else np.ascontiguousarray(normals, pts.dtype)
     check(lib.t3d_write_ply_h(str(path).encode(), _np_ptr(pts), int(pts.dtype == np.float64), _np_ptr(cols),
                               _np_ptr(nr), n, int(layout)))
+
+
+def write_ply_mesh(path, vertices, triangles, colors=None, normals=None):
+    """Triangle mesh -> .ply in Open3D's write_triangle_mesh layout (binary LE, double xyz [normals],
+    uchar rgb, `list uchar uint vertex_indices`).  Accepts torch (any device) or NumPy arrays."""
+    def host(a, dt):
+        if a is None:
+            return None
+        if hasattr(a, "detach"):
+            a = a.detach().cpu().numpy()
+        return np.ascontiguousarray(a, dt)
+    v = host(vertices, np.float32)
+    t = host(triangles, np.int32)
+    c = host(colors, np.uint8)
+    nr = host(normals, np.float32)
+    Path(path).parent.mkdir(parents=True, exist_ok=True)
+    check(_lib.load().t3d_write_ply_mesh_h(str(path).encode(), _np_ptr(v), _np_ptr(nr), _np_ptr(c), len(v),
+                                           _np_ptr(t), len(t)))
