@@ -257,7 +257,7 @@ def main():
         emit("K7 estimate_normals knn=30", "points", M, ms, 24 * M,
              cpu={"points_per_s": ns / cpu_s, "cores": cores, "sample": f"first {ns} points"})
     del pts, rgb
-    if only and not (only & {"K4", "K6", "K8", "K9"}):
+    if only and not (only & {"K4", "K6", "K8", "K9", "K10"}):
         return
 
     # ------------------------------------------------------------------ K4 / K6 on a fused volume
@@ -290,6 +290,30 @@ def main():
     emit("K6 extract_points thr=1", "blocks", nb, ms, 20 * 512 * nb + 27 * npts,
          cpu={"blocks_per_s": ov.num_blocks / cpu_s, "cores": cores, "sample": f"{ov.num_blocks} blocks ({nf_cpu} frames fused)"},
          surface_points=npts)
+
+    # ------------------------------------------------------------------ K10 triangle mesh
+    if want("K10"):
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(vol.lib.t3d_tsdf_extract_mesh(vol.handle, 1.0, None, None, None, 0, None, 0, _ptr(cnt), _stream()))
+        nv, nt = cnt.tolist()
+        mxyz = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        mnrm = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        mrgb = torch.empty((nv, 3), dtype=torch.uint8, device=dev)
+        mtri = torch.empty((nt, 3), dtype=torch.int32, device=dev)
+
+        def k10(i):
+            check(vol.lib.t3d_tsdf_extract_mesh(vol.handle, 1.0, _ptr(mxyz), _ptr(mnrm), _ptr(mrgb), nv, _ptr(mtri), nt,
+                                                _ptr(cnt), _stream()))
+        ms = gpu_time(k10, 10)
+        t0 = time.perf_counter()
+        om = ov.extract_mesh(1.0)
+        cpu_s = time.perf_counter() - t0
+        emit("K10 extract_mesh thr=1 (vertex + triangle kernels, incl. block-count D2H)", "blocks", nb, ms,
+             8 * 512 * nb + 27 * nv + 12 * nt + 2 * 4 * 512 * nb,
+             cpu={"blocks_per_s": ov.num_blocks / cpu_s, "cores": 1, "sample": f"{ov.num_blocks} blocks ({nf_cpu} frames fused), "
+                  f"{len(om[0])} vertices, {len(om[3])} triangles"},
+             vertices=nv, triangles=nt)
+        del mxyz, mnrm, mrgb, mtri
 
     def k4(i):
         vol.touch(depth[i % NF], K4, poses[i % NF], 1.0, 5.0)

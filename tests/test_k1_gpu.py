@@ -157,3 +157,70 @@ def test_capacity_and_argument_errors(ctx):
         ctx.backproject(d, None, fx=1., fy=1., cx=0., cy=0., out_xyz=small)
     with pytest.raises(T3DError):
         ctx.backproject(d, None, fx=1., fy=1., cx=0., cy=0., subsample=0)
+
+
+def _misaligned(t):
+    """Same values at an address that is NOT 16-byte aligned: forces the generic K1 kernel."""
+    import torch
+    flat = torch.empty(t.numel() + 16, dtype=t.dtype, device=t.device)
+    off = 1 if t.element_size() >= 4 else 3
+    view = flat[off:off + t.numel()].view(t.shape)
+    view.copy_(t)
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    return view
+
+
+@pytest.mark.parametrize("mode", ["f32", "f64scale", "f64depth"])
+@pytest.mark.parametrize("rgb_f32,with_pose,with_conf", [(False, True, False), (True, False, True), (False, False, True)])
+def test_streaming_kernel_equals_generic_kernel(ctx, oracle, mode, rgb_f32, with_pose, with_conf):
+    """The s = 1 TMA-staged kernel (16-byte aligned frames) and the generic kernel (any alignment)
+    must agree bit for bit in every mode, on sizes with many full tiles + a ragged last tile."""
+    import torch
+    H, W = 397, 1083                                    # 429 951 px = 209 full tiles + 1919 px, rows wrap inside threads
+    fx, fy, cx, cy = 1719.0, 1719.0, W / 2, H / 2
+    depth, bgr, T = ctx.synth_frame(1, 3, H, W, fx, fy, cx, cy)
+    rng = np.random.default_rng(11)
+    conf = torch.from_numpy((rng.uniform(size=(H, W)) > 0.25).astype(np.uint8)).cuda() if with_conf else None
+    pose = (T[:, :3].copy(), T[:, 3:4].copy()) if with_pose else None
+    kw = dict(fx=fx, fy=fy, cx=cx, cy=cy, pose=pose, rgb_out_f32=rgb_f32, scale=1.37, min_depth=0.2, max_depth=40.0,
+              scale_is_f64=(mode != "f32"))
+    d = depth.double() if mode == "f64depth" else depth
+    assert d.data_ptr() % 16 == 0 and bgr.data_ptr() % 16 == 0
+    a = ctx.backproject(d, bgr, conf_mask=conf, **kw)
+    b = ctx.backproject(_misaligned(d), _misaligned(bgr), conf_mask=None if conf is None else _misaligned(conf), **kw)
+    n = int(a[2].item())
+    assert n == int(b[2].item()) and 1000 < n < H * W
+    assert torch.equal(a[0][:n].view(torch.int32), b[0][:n].view(torch.int32))
+    assert torch.equal(a[1][:n], b[1][:n])
+    if mode != "f64depth" and not rgb_f32:
+        dm = depth.cpu().numpy()
+        if conf is not None:
+            dm = np.where(conf.cpu().numpy() > 0, dm, 0).astype(np.float32)
+        o_xyz, o_rgb = oracle.backproject(dm, bgr.cpu().numpy(), fx, fy, cx, cy, scale=1.37, f64_mask=(mode != "f32"),
+                                          min_depth=0.2, max_depth=40.0, pose=pose)
+        assert n == len(o_xyz)
+        assert np.array_equal(a[1][:n].cpu().numpy(), o_rgb)
+        assert close(a[0][:n].cpu().numpy(), o_xyz)
+
+
+def test_streaming_batch_full_size(ctx, oracle):
+    """3 x 1080p frames through t3d_backproject_batch (streaming kernel, tickets across frames)."""
+    import torch
+    H, W = 1920, 1080
+    fx, fy, cx, cy = 1719.0, 1719.0, 540.0, 960.0
+    depths, bgrs, poses = [], [], []
+    for i in range(3):
+        d, c, T = ctx.synth_frame(1, i, H, W, fx, fy, cx, cy)
+        if i == 1:
+            d[: H // 2] = 0.0
+        depths.append(d); bgrs.append(c); poses.append((T[:, :3].copy(), T[:, 3:4].copy()))
+    frames = ctx.make_backproject_frames(depths, bgrs, poses)
+    xyz, rgb, offs = ctx.backproject_batch(frames, 3, H, W, fx=fx, fy=fy, cx=cx, cy=cy, subsample=1)
+    offs = offs.cpu().numpy()
+    for i in range(3):
+        o_xyz, o_rgb = oracle.backproject(depths[i].cpu().numpy(), bgrs[i].cpu().numpy(), fx, fy, cx, cy, pose=poses[i])
+        a, b = int(offs[i]), int(offs[i + 1])
+        assert b - a == len(o_xyz)
+        assert np.array_equal(rgb[a:b].cpu().numpy(), o_rgb)
+        got = xyz[a:b].cpu().numpy()
+        assert close(got, o_xyz) and (got.view(np.uint32) == o_xyz.view(np.uint32)).mean() > 0.9999
