@@ -229,9 +229,21 @@ def run_ours(args):
             router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
 
     route_events = []
+    overlap = (router is not None and args.router == "p2p" and not args.no_overlap and not args.serial_batches
+               and -(-F // B) >= 3 and B >= int(np.ceil(DEPTH_MAX / 0.25)) + 2)
+    views_ov = None
+    if overlap:
+        order = P2PBlockRouter.overlap_order(F, B)
+        views_ov = vol.make_frame_views([depth_all[i] for i in order], [bgr_all[i] for i in order],
+                                        [KINTR] * F, [poses[i] for i in order])
 
     def step():
         vol.reset()
+        if overlap:
+            # tail batch first -> export/fence/merge on the router's stream underneath the fusion of
+            # the other batches -> head batch last (see P2PBlockRouter.fuse_overlapped)
+            router.fuse_overlapped(views_ov, F, H, W, B, False, 1.0, DEPTH_MAX)
+            return
         if args.serial_batches:
             for s in range(0, F, B):
                 vol.integrate_views(views, s, min(B, F - s), H, W, False, 1.0, DEPTH_MAX)
@@ -312,6 +324,9 @@ def run_ours(args):
 
     # ---- e2e: host buffers -> H2D -> fuse -> D2H result, through the public API
     e2e = None if args.no_e2e else run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist if world > 1 else None)
+    e2e_u16 = None
+    if e2e is not None and world == 1 and args.workload == "cfg2":
+        e2e_u16 = run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, None, u16=True)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -328,12 +343,19 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "blocks_per_gpu": int(nblocks), "batch_frames": B,
         }
+        if e2e_u16 is not None:
+            line["e2e_u16mm_depth"] = e2e_u16
         if router is not None:
             if args.router == "p2p":
                 sent, dropped = router.stats()
                 line["routing"] = {"blocks_sent_rank0": int(sum(sent)), "records_dropped_rank0": int(dropped),
                                    "bytes_sent_rank0": int(sum(sent)) * 4 * vol.RECORD_WORDS,
-                                   "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
+                                   "route_ms_per_step_rank0": (float(np.mean([a.elapsed_time(b) for a, b in route_events]))
+                                                               if route_events else None),
+                                   "overlapped_with_fusion": bool(overlap),
+                                   "batch_order": ("last batch (frames that reach past the slab) first, routing on a side "
+                                                   "stream underneath the other batches, first batch last after the merge"
+                                                   if overlap else "ascending, routing after fusion"),
                                    "transport": "export kernel stores 10 KiB block records straight into the owner's "
                                                 "memory over NVLink (CUDA IPC peer mapping); 4-byte NCCL all_reduce as "
                                                 "the export->merge fence; owner merges from its own HBM"}
@@ -348,20 +370,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist):
+def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist, u16=False):
     """Frames start in pinned host memory; every step copies all of them to the GPU
     (double-buffered chunks on a copy stream, overlapped with fusion), fuses, and reads
-    the step's result (voxel-update / block counters) back to the host."""
+    the step's result (voxel-update / block counters) back to the host.
+    u16=True: the host depth is the reference's on-disk format, 16-bit millimetres
+    (`(depth * 1000).astype(uint16)`, dp:919-921; read back as raw / 1000, d2r:85-90) — 2 B/pixel
+    over PCIe, decoded inside K4/K5 (depth_scale = 1000).  Reported next to, never instead of, the
+    float32 number: the fused volume differs by the millimetre quantisation."""
     import torch
     dev = ctx.device
     F, B = args.frames, args.batch
-    h_depth = torch.empty((F, H, W), dtype=torch.float32, pin_memory=True)
+    ddt = torch.uint16 if u16 else torch.float32
+    h_depth = torch.empty((F, H, W), dtype=ddt, pin_memory=True)
     h_bgr = torch.empty((F, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    h_depth.copy_(depth_all)
+    if u16:
+        for i in range(F):
+            h_depth[i].copy_(ctx.depth_f32_to_u16(depth_all[i], 1000.0))
+    else:
+        h_depth.copy_(depth_all)
     h_bgr.copy_(bgr_all)
     torch.cuda.synchronize()
     nbuf = 2
-    d_depth = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    d_depth = [torch.empty((B, H, W), dtype=ddt, device=dev) for _ in range(nbuf)]
     d_bgr = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
@@ -385,7 +416,7 @@ def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist):
                 d_bgr[b][:n].copy_(h_bgr[s:s + n], non_blocking=True)
                 copied[ci].record(copy_stream)
             main.wait_event(copied[ci])
-            vol.integrate_views(views[ci], 0, n, H, W, False, 1.0, DEPTH_MAX)
+            vol.integrate_views(views[ci], 0, n, H, W, u16, 1000.0 if u16 else 1.0, DEPTH_MAX)
             freed[b].record(main)
         return vol.counters()          # synchronous D2H read of the step's result
 
@@ -407,8 +438,8 @@ def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist):
         ms = float(t.item())
     del h_depth, h_bgr
     return {"value": F * world * steps / (ms * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": int(F * H * W * 7), "d2h_bytes_per_step": 40, "steps": steps,
-            "ms_per_step": ms / steps, "result": res,
+            "h2d_bytes_per_step": int(F * H * W * (5 if u16 else 7)), "d2h_bytes_per_step": 40, "steps": steps,
+            "ms_per_step": ms / steps, "result": res, "depth_dtype": "u16 millimetres" if u16 else "f32 metres",
             "api": "TSDFVolume.integrate_views over pinned-host frames (H2D double-buffered) + counters() D2H"}
 
 
@@ -542,6 +573,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     ap.add_argument("--serial-batches", action="store_true", help="(tuning) no K4/K5 overlap")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="(N > 1, p2p router) route after fusion instead of underneath it")
     ap.add_argument("--router", choices=["p2p", "nccl"], default="p2p",
                     help="N>1 block routing: peer-memory stores over NVLink (default) or NCCL all_to_all")
     ap.add_argument("--region-records", type=int, default=16384,

@@ -199,6 +199,29 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
                                 int depth_is_u16, float depth_scale,
                                 float depth_max, t3d_stream stream);
 
+/* The same pipeline with hooks, for block routing that overlaps fusion (callers put
+ * the frames whose blocks must travel into batch 0 and the frames that meet incoming blocks
+ * into the last batch):
+ *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch 0 — every
+ *     block batch 0 touches exists and no allocation is in flight at that point;
+ *   after_batch0(user, event): called ON THE HOST, inside this call, right after K5 of batch 0
+ *     was enqueued; `event` (a cudaEvent_t) completes with it.  The callee enqueues its own
+ *     work on another stream (t3d_stream_wait_event) and records its completion event;
+ *   wait_before_last (cudaEvent_t, nullable): K4 and K5 of the last batch wait for it.
+ * Needs at least 2 batches when any hook is given. */
+typedef void (*t3d_sequence_hook)(void* user, void* event_after_batch0);
+int t3d_tsdf_integrate_sequence_hooked(t3d_tsdf* v, const t3d_frame_view* frames_h,
+                                       int n_frames, int batch, int H, int W,
+                                       int depth_is_u16, float depth_scale, float depth_max,
+                                       int32_t* nblocks_after_touch0,
+                                       t3d_sequence_hook after_batch0, void* user,
+                                       void* wait_before_last, t3d_stream stream);
+/* Timing-less CUDA events for the hooks above (handles are cudaEvent_t). */
+int t3d_event_create(void** out_event);
+int t3d_event_destroy(void* event);
+int t3d_event_record(void* event, t3d_stream stream);
+int t3d_stream_wait_event(t3d_stream stream, void* event);
+
 /* K4 alone: unique block keys touched by one frame (R4).  out_keys: cap*3
  * int32; out_n device int64.  Does not modify the volume. */
 int t3d_tsdf_touch(t3d_tsdf* v, const t3d_frame_view* frame_h, int H, int W,
@@ -271,12 +294,15 @@ int t3d_tsdf_merge_records(t3d_tsdf* v, const float* records, int64_t b,
  * with t3d_ipc_open), the region reserved for records coming from THIS rank; peer_counts_h[d]
  * the int32 header slot there for this rank's record count, written by the last CTA.
  * local_fill: device int32[world + 2] scratch ([world] = CTA ticket, [world+1] = records that
- * did not fit).  The owners then call t3d_tsdf_merge_records_dev on their own memory after a
- * barrier.  Asynchronous; no staging copy, no collective on the data path. */
+ * did not fit).  n_blocks_dev (device int32, nullable): only blocks [0, *n_blocks_dev) are
+ * examined (see t3d_tsdf_integrate_sequence_hooked).  The owners then call
+ * t3d_tsdf_merge_records_dev on their own memory after a barrier.  Asynchronous; no staging copy,
+ * no collective on the data path. */
 int t3d_tsdf_route_export_p2p(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
                               int self_rank, void* const* peer_regions_h,
                               int32_t* const* peer_counts_h, int64_t region_records,
-                              int32_t* local_fill, t3d_stream stream);
+                              int32_t* local_fill, const int32_t* n_blocks_dev,
+                              t3d_stream stream);
 /* t3d_tsdf_merge_records with the record count read from device memory (<= max_b). */
 int t3d_tsdf_merge_records_dev(t3d_tsdf* v, const float* records, const int32_t* count_dev,
                                int64_t max_b, t3d_stream stream);

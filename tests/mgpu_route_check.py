@@ -70,11 +70,47 @@ def main():
     b.route()
     torch.cuda.synchronize()
     ok = ok and same()[0] and b.stats()[1] == 0
-    res = torch.tensor([int(ok), int(ok2)], device="cuda")
+    # ---- routing that overlaps fusion (tail batch first, merge before the head batch)
+    F2, B2 = 60, 24
+    fr = [S.synth_frame(0, rank * F2 + i, H, W, *K, noise_sigma=0.002) for i in range(F2)]
+    dd = [torch.from_numpy(f[0]).cuda() for f in fr]
+    cc = [torch.from_numpy(f[1]).cuda() for f in fr]
+    vo = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
+    vs = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
+    ro = D.P2PBlockRouter(vo, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
+    rs = D.P2PBlockRouter(vs, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
+    order = D.P2PBlockRouter.overlap_order(F2, B2)
+    views_o = vo.make_frame_views([dd[i] for i in order], [cc[i] for i in order], [K] * F2, [fr[i][2] for i in order])
+    views_s = vs.make_frame_views(dd, cc, [K] * F2, [f[2] for f in fr])
+    ok3 = True
+    for rep in range(3):                                   # both receive buffers, steady state
+        vo.reset()
+        vs.reset()
+        ro.fuse_overlapped(views_o, F2, H, W, B2, False, 1.0, 5.0)
+        vs.integrate_sequence(views_s, F2, H, W, B2, False, 1.0, 5.0)
+        rs.route()
+        torch.cuda.synchronize()
+        lo2, hi2 = D.block_owner_range(rank, world, ro.slab_blocks)
+        lo2, hi2 = max(lo2, -(1 << 20)), min(hi2, 1 << 20)
+        eo = by_key(*[x.cpu().numpy() for x in vo.export_blocks_range(2, lo2, hi2)])
+        es = by_key(*[x.cpu().numpy() for x in vs.export_blocks_range(2, lo2, hi2)])
+        ok3 = ok3 and np.array_equal(eo[0], es[0]) and np.array_equal(eo[2], es[2])      # keys, integer weights
+        ok3 = ok3 and float(np.abs(eo[1] - es[1]).max()) < 1e-4 and ro.stats()[1] == 0 and ro.stats()[0] == rs.stats()[0]
+    ref2 = TSDFVolume(0.01, 0.04, block_capacity=480000, ctx=ctx)
+    for r in range(world):
+        for i in range(F2):
+            d, c, T = S.synth_frame(0, r * F2 + i, H, W, *K, noise_sigma=0.002)
+            ref2.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
+    rk2, rt2, rw2, _ = by_key(*[x.cpu().numpy() for x in ref2.export_blocks_range(2, lo2, hi2)])
+    ok3 = ok3 and np.array_equal(eo[0], rk2) and np.array_equal(eo[2], rw2) and float(np.abs(eo[1] - rt2).max()) < 1e-4
+    res = torch.tensor([int(ok), int(ok2), int(ok3)], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"MGPU_ROUTE_CHECK p2p==nccl {bool(res[0].item())} owned==serial {bool(res[1].item())} "
-              f"sent_rank0={sent} blocks_rank0={vols[1].num_blocks}", flush=True)
+              f"overlapped==serial {bool(res[2].item())} sent_rank0={sent} overlapped_sent_rank0={ro.stats()[0]} "
+              f"blocks_rank0={vols[1].num_blocks}", flush=True)
+    ro.close()
+    rs.close()
     b.close()
     dist.destroy_process_group()
     sys.exit(0 if res.min().item() == 1 else 1)

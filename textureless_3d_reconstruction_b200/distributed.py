@@ -16,6 +16,8 @@ world_size-2 tests (tests/test_distributed_cpu.py) and under NCCL on the GPUs.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 
@@ -180,6 +182,7 @@ class P2PBlockRouter:
         self.fill = torch.zeros(world + 2, dtype=torch.int32, device=self.ctx.device)
         self.token = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
         self.step = 0
+        self._side = self._done = self._snap = None
         self._regions = [(C.c_void_p * world)() for _ in range(2)]
         self._counts = [(C.c_void_p * world)() for _ in range(2)]
         for parity in range(2):
@@ -187,7 +190,7 @@ class P2PBlockRouter:
                 self._regions[parity][d] = self.peers[parity][d] + self.HEADER + rank * self.region_bytes
                 self._counts[parity][d] = self.peers[parity][d] + 4 * rank
 
-    def route(self):
+    def route(self, n_blocks_dev=None):
         import ctypes as C
         import torch.distributed as dist
         from . import _lib
@@ -198,7 +201,7 @@ class P2PBlockRouter:
         self.step += 1
         _lib.check(self.lib.t3d_tsdf_route_export_p2p(self.vol.handle, self.AXIS, self.slab_blocks, self.world, self.rank,
                                                       self._regions[par], self._counts[par], self.region_records,
-                                                      _ptr(self.fill), _stream()))
+                                                      _ptr(self.fill), _ptr(n_blocks_dev), _stream()))
         dist.all_reduce(self.token, group=self.group)     # every rank's export precedes every rank's merge
         base = self.local[par]
         for s in range(self.world):
@@ -208,6 +211,52 @@ class P2PBlockRouter:
                     self.region_records, _stream()))
         _lib.check(self.lib.t3d_memset_async(C.c_void_p(base), 0, self.HEADER, _stream()))
 
+    # ---- routing that overlaps fusion -------------------------------------------------------------
+    # The frames whose blocks must travel (the last ceil(depth_max / frame_advance) + 2 of a rank's
+    # slab: only they reach past its end) are fused FIRST, then export -> fence -> merge run on the
+    # router's own stream underneath the fusion of the other batches; the batch that meets the
+    # incoming blocks (the slab's first frames) is fused LAST, after the merge.  Unit-weight running
+    # means do not depend on the order in which frames arrive (weights exact, tsdf to rounding).
+    @staticmethod
+    def overlap_order(n_frames, batch):
+        """Frame order for fuse_overlapped: batches in descending order, frames ascending inside."""
+        order = []
+        hi = n_frames
+        while hi > 0:
+            lo = max(0, hi - batch)
+            order.extend(range(lo, hi))
+            hi = lo
+        return order
+
+    def fuse_overlapped(self, views_reordered, n_frames, H, W, batch, depth_is_u16=False, depth_scale=1.0,
+                        depth_max=5.0, frame_advance=0.25):
+        """Fuse `views_reordered` (frame views in overlap_order) and route in the same pass.  The
+        current stream ends ordered after fusion AND routing."""
+        import torch
+        from . import _lib
+        from .runtime import _stream
+        nb = -(-n_frames // batch)
+        reach = int(np.ceil(depth_max / frame_advance)) + 2
+        if nb < 3 or batch < reach:
+            raise ValueError(f"overlapped routing needs >= 3 batches of >= {reach} frames (got {nb} x {batch})")
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.ctx.device)
+            self._done = C.c_void_p()
+            _lib.check(self.lib.t3d_event_create(C.byref(self._done)))
+            self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        side = self._side
+
+        def after_batch0(ev):
+            h = C.c_void_p(side.cuda_stream)
+            _lib.check(self.lib.t3d_stream_wait_event(h, ev))
+            with torch.cuda.stream(side):
+                self.route(n_blocks_dev=self._snap)
+            _lib.check(self.lib.t3d_event_record(self._done, h))
+
+        self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, after_batch0,
+                                           self._done, depth_is_u16, depth_scale, depth_max)
+        _lib.check(self.lib.t3d_stream_wait_event(_stream(), self._done))
+
     def stats(self):
         """(records sent per destination, records that did not fit) of the last route — synchronises."""
         f = self.fill.cpu().tolist()
@@ -215,6 +264,9 @@ class P2PBlockRouter:
         return sent, f[self.world + 1]
 
     def close(self):
+        if self._done is not None:
+            self.lib.t3d_event_destroy(self._done)
+            self._done = None
         for parity in range(2):
             for d in range(self.world):
                 if d != self.rank:

@@ -411,6 +411,27 @@ class TSDFVolume:
                                                    int(depth_is_u16), float(depth_scale), float(depth_max),
                                                    _stream()))
 
+    def integrate_sequence_hooked(self, views, n_frames, H, W, batch, nblocks_dev, after_batch0, wait_event,
+                                  depth_is_u16=False, depth_scale=1.0, depth_max=5.0, start=0):
+        """integrate_sequence with the routing hooks of t3d_tsdf_integrate_sequence_hooked:
+        nblocks_dev (int32[1] CUDA tensor) receives the block count after K4 of batch 0,
+        after_batch0(event_handle) is called on the host once K5 of batch 0 is enqueued, and the
+        last batch waits for wait_event (a handle from t3d_event_create)."""
+        sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
+        err = []
+
+        def _cb(_user, ev):
+            try:
+                after_batch0(C.c_void_p(ev))
+            except BaseException as e:  # noqa: BLE001 - must not propagate through the C frame
+                err.append(e)
+        cb = _lib.SEQUENCE_HOOK(_cb)
+        check(self.lib.t3d_tsdf_integrate_sequence_hooked(
+            self.handle, sub, int(n_frames), int(batch), int(H), int(W), int(depth_is_u16), float(depth_scale),
+            float(depth_max), _ptr(nblocks_dev), cb, None, wait_event, _stream()))
+        if err:
+            raise err[0]
+
     def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0):
         """Fuse one frame.  depth: (H,W) f32|u16 CUDA tensor; bgr: (H,W,3) u8 or None;
         K=(fx,fy,cx,cy); T_cw: world->camera 4x4 or 3x4."""
