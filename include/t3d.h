@@ -133,6 +133,29 @@ int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f64,
                          int64_t* out_m, double* out_min_bound_h,
                          t3d_stream stream);
 
+/* Sharded K2 (owner = hash(voxel index) mod G, all_to_all of per-voxel partial sums,
+ * owner merges).  Both calls take the GLOBAL grid: min_bound_h = min over all ranks - voxel/2,
+ * max_bound_h = max over all ranks (exact all_reduce of t3d_bounds), so that every rank computes
+ * identical voxel indices.
+ * t3d_voxel_partials: this rank's points -> one 56-byte record per locally occupied voxel
+ *   {int32 ix, iy, iz; uint32 count; double sum_x, sum_y, sum_z; uint32 sum_r, sum_g, sum_b, pad},
+ *   grouped by owner (`world` owners); out_counts: device int32[world] records per owner;
+ *   out_m: device int64 total.  capacity in records.
+ * t3d_voxel_merge_partials: records received from every rank -> the owner's voxels, outputs as
+ *   t3d_voxel_downsample.  f64 sums of f32 coordinates inside a voxel are exact, so the result is
+ *   bit-identical to a single-GPU run over the union of the points. */
+int t3d_voxel_partials(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, const uint8_t* rgb,
+                       int64_t n, double voxel, const double* min_bound_h,
+                       const double* max_bound_h, int world, void* out_records,
+                       int64_t capacity, int32_t* out_counts, int64_t* out_m,
+                       t3d_stream stream);
+int t3d_voxel_merge_partials(t3d_ctx* ctx, const void* records, int64_t n_records, int has_rgb,
+                             double voxel, const double* min_bound_h,
+                             const double* max_bound_h, int sorted, double* out_xyz,
+                             uint8_t* out_rgb, uint32_t* out_rgb_sum, uint32_t* out_count,
+                             int32_t* out_vox_idx, int64_t capacity, int64_t* out_m,
+                             t3d_stream stream);
+
 /* Min / max bound of a cloud (host result, synchronous). */
 int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t n,
                double* min_h, double* max_h, t3d_stream stream);
@@ -348,6 +371,14 @@ int t3d_tsdf_extract_mesh(t3d_tsdf* v, float weight_threshold, float* xyz, float
                           uint8_t* rgb, int64_t vertex_capacity, int32_t* tri,
                           int64_t triangle_capacity, int64_t* out_counts,
                           t3d_stream stream);
+
+/* K6 over the blocks with key[axis] in [lo, hi) only (each owner extracts its own slab;
+ * neighbour tests and gradients read every block present, i.e. the halo fetched from the
+ * neighbouring ranks).  Asynchronous apart from the block count. */
+int t3d_tsdf_extract_points_range(t3d_tsdf* v, int axis, int32_t lo, int32_t hi,
+                                  float weight_threshold, float* xyz, float* nrm,
+                                  uint8_t* rgb, int64_t capacity, int64_t* out_n,
+                                  t3d_stream stream);
 
 /* ------------------------------------------------------------------------- */
 /* K7 — normal estimation (north_star; Open3D estimate_normals KNN, R7).      */

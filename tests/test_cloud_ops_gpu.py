@@ -238,3 +238,48 @@ def test_voxel_downsample_full_size_properties(ctx, oracle):
     # colours: trunc(mean(c/255)*255) can flip by 1 LSB at exact integers (f64 summation order)
     dc = np.abs(g["colors"].cpu().numpy().astype(np.int16) - o["colors_u8"][oo].astype(np.int16))
     assert dc.max() <= 1 and (dc != 0).mean() < 0.02
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_voxel_partials_then_merge_equals_downsample(ctx, world):
+    """Sharded K2 building blocks on one GPU: split the cloud in `world` shards, take each shard's
+    per-voxel partial sums (records grouped by owner), hand every owner its records, merge — the
+    union of the owners' voxels is bit-identical to one voxel_downsample over all points."""
+    import torch
+    rng = np.random.default_rng(21)
+    n = 200_000
+    p = (rng.uniform(-2.0, 2.0, (n, 3)) * np.array([1.0, 0.6, 2.5])).astype(np.float32)
+    p[::11] = p[5]
+    c = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    xyz, rgb = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda()
+    voxel = 0.03
+    ref = ctx.voxel_downsample(xyz, rgb, voxel, sorted_output=True)
+    mn, mx = ctx.bounds(xyz)
+    minb = mn - voxel * 0.5
+    assert np.array_equal(minb, ref["min_bound"])
+    cuts = np.linspace(0, n, world + 1).astype(int)
+    inbox = [[] for _ in range(world)]
+    sent = 0
+    for r in range(world):
+        rec, counts = ctx.voxel_partials(xyz[cuts[r]:cuts[r + 1]].contiguous(), rgb[cuts[r]:cuts[r + 1]].contiguous(),
+                                         voxel, minb, mx, world)
+        cl = counts.cpu().tolist()
+        assert sum(cl) == rec.shape[0] and rec.shape[1] == 56
+        off = 0
+        for d in range(world):
+            inbox[d].append(rec[off:off + cl[d]])
+            off += cl[d]
+        sent += rec.shape[0]
+    outs = [ctx.voxel_merge_partials(torch.cat(inbox[d]).contiguous(), True, voxel, minb, mx) for d in range(world)]
+    assert sum(o["m"] for o in outs) == ref["m"] and sent >= ref["m"]
+    idx = torch.cat([o["idx"] for o in outs]).cpu().numpy()
+    pts = torch.cat([o["points"] for o in outs]).cpu().numpy()
+    col = torch.cat([o["colors"] for o in outs]).cpu().numpy()
+    cnt = torch.cat([o["count"] for o in outs]).cpu().numpy()
+    order = np.lexsort(idx[:, ::-1].T)
+    assert np.array_equal(idx[order], ref["idx"].cpu().numpy())                       # ascending (x,y,z) like sorted K2
+    assert np.array_equal(pts[order].view(np.uint64), ref["points"].cpu().numpy().view(np.uint64))   # bit-identical means
+    assert np.array_equal(col[order], ref["colors"].cpu().numpy())
+    assert np.array_equal(cnt[order], ref["count"].cpu().numpy())
+    # every owner holds only its own voxels, each voxel exactly once
+    assert len(np.unique(idx, axis=0)) == len(idx)

@@ -147,3 +147,114 @@ def test_solve_icp_update_matches_oracle(oracle):
     assert np.allclose(D.solve_icp_update(full[:27]), one["T"], atol=1e-10)
     # ill-posed system -> identity update (R8 det guard)
     assert np.array_equal(D.solve_icp_update(np.zeros(27)), np.eye(4))
+
+
+# ------------------------------------------------------------------ sharded K2 + gather
+VREC = np.dtype([("ix", "<i4"), ("iy", "<i4"), ("iz", "<i4"), ("cnt", "<u4"), ("sx", "<f8"), ("sy", "<f8"),
+                 ("sz", "<f8"), ("r", "<u4"), ("g", "<u4"), ("b", "<u4"), ("pad", "<u4")])
+assert VREC.itemsize == 56
+
+
+class NumpyCloudOps:
+    """CPU stand-in for runtime.Context in sharded_voxel_downsample: the same wire record, R2's
+    index rule (floor((p - minb) / v) in f64, true division) and sum-then-divide means."""
+
+    @staticmethod
+    def bounds(xyz):
+        a = xyz.numpy().astype(np.float64)
+        return a.min(0), a.max(0)
+
+    @staticmethod
+    def voxel_partials(xyz, rgb, v, minb, gmax, world):
+        p = xyz.numpy().astype(np.float64)
+        idx = np.floor((p - minb) / v).astype(np.int64)
+        u, inv = np.unique(idx, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        rec = np.zeros(len(u), VREC)
+        rec["ix"], rec["iy"], rec["iz"] = u[:, 0], u[:, 1], u[:, 2]
+        rec["cnt"] = np.bincount(inv, minlength=len(u))
+        for c, f in enumerate(("sx", "sy", "sz")):
+            rec[f] = np.bincount(inv, weights=p[:, c], minlength=len(u))
+        if rgb is not None:
+            col = rgb.numpy().astype(np.float64)
+            for c, f in enumerate(("r", "g", "b")):
+                rec[f] = np.bincount(inv, weights=col[:, c], minlength=len(u)).astype(np.uint32)
+        owner = (u[:, 0] * 73856093 ^ u[:, 1] * 19349663 ^ u[:, 2] * 83492791) % world
+        order = np.argsort(owner, kind="stable")
+        counts = np.bincount(owner, minlength=world).astype(np.int32)
+        raw = np.frombuffer(rec[order].tobytes(), np.uint8).reshape(-1, 56).copy()
+        return torch.from_numpy(raw), torch.from_numpy(counts)
+
+    @staticmethod
+    def voxel_merge_partials(records, has_rgb, v, minb, gmax, sorted_output=True):
+        rec = np.frombuffer(records.numpy().tobytes(), VREC)
+        idx = np.stack([rec["ix"], rec["iy"], rec["iz"]], 1).astype(np.int64)
+        u, inv = np.unique(idx, axis=0, return_inverse=True)       # np.unique sorts lexicographically
+        inv = inv.reshape(-1)
+        cnt = np.bincount(inv, weights=rec["cnt"], minlength=len(u))
+        pts = np.stack([np.bincount(inv, weights=rec[f], minlength=len(u)) for f in ("sx", "sy", "sz")], 1) / cnt[:, None]
+        out = dict(points=torch.from_numpy(pts), idx=torch.from_numpy(u.astype(np.int32)),
+                   count=torch.from_numpy(cnt.astype(np.int32)), colors=None, rgb_sum=None, m=len(u))
+        if has_rgb:
+            s = np.stack([np.bincount(inv, weights=rec[f], minlength=len(u)) for f in ("r", "g", "b")], 1)
+            out["rgb_sum"] = torch.from_numpy(s.astype(np.int32))
+            out["colors"] = torch.from_numpy((s / 255.0 / cnt[:, None] * 255.0).astype(np.uint8))
+        return out
+
+
+def _cloud(rank_count=2, n=4000):
+    rng = np.random.default_rng(77)
+    p = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+    p[::7] = p[3]                                       # duplicates that land on both ranks
+    c = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    cut = [0, n // 3, n] if rank_count == 2 else [0, n]
+    return p, c, cut
+
+
+def _k2_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, c, cut = _cloud(world)
+        xs, cs = torch.from_numpy(p[cut[rank]:cut[rank + 1]]), torch.from_numpy(c[cut[rank]:cut[rank + 1]])
+        out = D.sharded_voxel_downsample(NumpyCloudOps, xs, cs, 0.05)
+        rows = torch.cat([out["idx"].double(), out["points"], out["count"].double().unsqueeze(1),
+                          out["rgb_sum"].double()], 1)
+        allrows = D.gather_rows(rows, dst=0)
+        # a rank without points takes part in every collective
+        empty = D.sharded_voxel_downsample(NumpyCloudOps, xs[:0] if rank == 1 else xs, cs[:0] if rank == 1 else cs, 0.05)
+        q.put((rank, None if allrows is None else allrows.numpy(), out["m"], empty["m"], out["records_sent"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_voxel_downsample_world2(oracle):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_k2_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p, c, cut = _cloud(world)
+    ref = oracle.voxel_downsample(p.astype(np.float64), c, 0.05)
+    rows = res[0][1]
+    assert res[1][1] is None and rows.shape[0] == len(ref["points"]) == res[0][2] + res[1][2]
+    order = np.lexsort(rows[:, [2, 1, 0]].T)
+    rows = rows[order]
+    ro = np.lexsort(ref["idx"][:, ::-1].T)
+    assert np.array_equal(rows[:, :3].astype(np.int32), ref["idx"][ro])             # voxel index set bit-exact
+    assert np.array_equal(rows[:, 6].astype(np.uint32), ref["count"][ro])
+    assert np.allclose(rows[:, 3:6], ref["points"][ro], rtol=1e-12, atol=1e-12)
+    # rank 0 alone (rank 1 contributed nothing) == oracle on rank 0's shard
+    ref0 = oracle.voxel_downsample(p[cut[0]:cut[1]].astype(np.float64), c[cut[0]:cut[1]], 0.05)
+    assert res[0][3] + res[1][3] == len(ref0["points"])
+    assert res[0][4] > 0

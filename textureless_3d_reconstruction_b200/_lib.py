@@ -74,6 +74,8 @@ _SIGS = {
     "t3d_backproject_batch": (_I, [_VP, C.POINTER(BackprojectFrame), _I, C.POINTER(BackprojectParams), _VP, _VP, _I64,
                                    _VP, _VP]),
     "t3d_voxel_downsample": (_I, [_VP, _VP, _I, _VP, _I64, _D, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    "t3d_voxel_partials": (_I, [_VP, _VP, _I, _VP, _I64, _D, _VP, _VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "t3d_voxel_merge_partials": (_I, [_VP, _VP, _I64, _I, _D, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_bounds": (_I, [_VP, _VP, _I, _I64, _VP, _VP, _VP]),
     "t3d_statistical_outlier": (_I, [_VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),
     "t3d_compact_rows": (_I, [_VP, _VP, _I64, C.c_int32, _VP, _VP, _VP, _VP]),
@@ -109,6 +111,7 @@ _SIGS = {
     "t3d_tsdf_merge_blocks": (_I, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "t3d_tsdf_extract_points": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_extract_points_view": (_I, [_VP, C.POINTER(FrameView), _I, _I, _F, _F, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    "t3d_tsdf_extract_points_range": (_I, [_VP, _I, C.c_int32, C.c_int32, _F, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_tsdf_extract_mesh": (_I, [_VP, _F, _VP, _VP, _VP, _I64, _VP, _I64, _VP, _VP]),
     "t3d_write_ply_mesh_h": (_I, [C.c_char_p, _VP, _VP, _VP, _I64, _VP, _I64]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),

@@ -227,6 +227,121 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Sharded K2: a rank's per-voxel partial sums travel as 56-byte records; the owner
+// (mix64(voxel index) mod world) adds the partials of every rank.  f64 sums of f32 coordinates
+// inside one voxel are exact, so the merged means equal the single-GPU means bit for bit.
+// ---------------------------------------------------------------------------
+struct __align__(8) VoxRec {  // wire format, 7 x 8 bytes
+  int ix, iy, iz;
+  unsigned cnt;
+  double sx, sy, sz;
+  unsigned r, g, b, pad;
+};
+static_assert(sizeof(VoxRec) == 56, "VoxRec is the 56-byte wire record");
+
+__device__ __forceinline__ bool rec_key(const VoxRec& q, const VoxGrid& g, const VoxTable& tb,
+                                        unsigned long long& key) {
+  if (!(q.ix >= 0 && (double)q.ix < g.lim_x && q.iy >= 0 && (double)q.iy < g.lim_y && q.iz >= 0 &&
+        (double)q.iz < g.lim_z)) {
+    tb.flags[1] = 1;
+    return false;
+  }
+  key = ((unsigned long long)(unsigned)q.ix << tb.sh_x) | ((unsigned long long)(unsigned)q.iy << tb.sh_y) |
+        (unsigned long long)(unsigned)q.iz;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+    rec_keys_kernel(const VoxRec* __restrict__ recs, long long n, const __grid_constant__ VoxGrid g,
+                    const __grid_constant__ VoxTable tb) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long key = 0;
+    if (!rec_key(recs[i], g, tb, key)) continue;
+    unsigned long long slot = mix64(key) & tb.mask;
+    bool placed = false;
+    for (unsigned long long probe = 0; probe <= tb.mask; ++probe) {
+      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + slot));
+      if (k == T3D_KEY_EMPTY) {
+        k = atomicCAS(tb.keys + slot, T3D_KEY_EMPTY, key);
+        if (k == T3D_KEY_EMPTY) {
+          const unsigned long long id = atomicAdd(tb.counter, 1ull);
+          tb.ids[slot] = (unsigned)id;
+          tb.key_of_id[id] = key;
+          placed = true;
+          break;
+        }
+      }
+      if (k == key) { placed = true; break; }
+      slot = (slot + 1) & tb.mask;
+    }
+    if (!placed) tb.flags[0] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    rec_accum_kernel(const VoxRec* __restrict__ recs, long long n, int has_rgb,
+                     const __grid_constant__ VoxGrid g, const __grid_constant__ VoxTable tb) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const VoxRec q = recs[i];
+    unsigned long long key = 0;
+    if (!rec_key(q, g, tb, key)) continue;
+    unsigned long long slot = mix64(key) & tb.mask;
+    while (tb.keys[slot] != key) slot = (slot + 1) & tb.mask;
+    VoxAcc* a = tb.acc + tb.ids[slot];
+    atomicAdd(&a->sx, q.sx); atomicAdd(&a->sy, q.sy); atomicAdd(&a->sz, q.sz);
+    if (has_rgb) { atomicAdd(&a->r, q.r); atomicAdd(&a->g, q.g); atomicAdd(&a->b, q.b); }
+    atomicAdd(&a->cnt, q.cnt);
+  }
+}
+
+__device__ __forceinline__ int rec_owner(int ix, int iy, int iz, int world) {
+  return (int)(mix64(pack_key(ix, iy, iz)) % (unsigned long long)world);
+}
+
+// pass 0: per-owner counts; pass 1: scatter (offsets = exclusive scan of the counts, done by
+// thread 0 of the first CTA of pass 1's predecessor kernel below)
+__global__ void __launch_bounds__(256)
+    partials_count_kernel(const __grid_constant__ VoxTable tb, long long m, int world, int* counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = tb.key_of_id[i];
+    const int ix = (int)(k >> tb.sh_x);
+    const int iy = (int)((k >> tb.sh_y) & ((1ull << (tb.sh_x - tb.sh_y)) - 1ull));
+    const int iz = (int)(k & ((1ull << tb.sh_y) - 1ull));
+    atomicAdd(counts + rec_owner(ix, iy, iz, world), 1);
+  }
+}
+
+__global__ void partials_offsets_kernel(const int* counts, int world, int* offs, int* fill) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    for (int d = 0; d < world; ++d) { offs[d] = run; run += counts[d]; fill[d] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    partials_scatter_kernel(const __grid_constant__ VoxTable tb, long long m, int world, int has_rgb,
+                            const int* offs, int* fill, VoxRec* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = tb.key_of_id[i];
+    VoxRec q;
+    q.ix = (int)(k >> tb.sh_x);
+    q.iy = (int)((k >> tb.sh_y) & ((1ull << (tb.sh_x - tb.sh_y)) - 1ull));
+    q.iz = (int)(k & ((1ull << tb.sh_y) - 1ull));
+    const VoxAcc a = tb.acc[i];
+    q.cnt = a.cnt;
+    q.sx = a.sx; q.sy = a.sy; q.sz = a.sz;
+    q.r = has_rgb ? a.r : 0u; q.g = has_rgb ? a.g : 0u; q.b = has_rgb ? a.b : 0u;
+    q.pad = 0u;
+    const int o = rec_owner(q.ix, q.iy, q.iz, world);
+    out[offs[o] + atomicAdd(fill + o, 1)] = q;
+  }
+}
+
 // order[i] = voxel id written at output row i (identity when unsorted)
 __global__ void voxel_finalize_kernel(const __grid_constant__ VoxTable tb,
                                       const unsigned* __restrict__ order, long long m,
@@ -500,25 +615,39 @@ extern "C" int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t
   return T3D_OK;
 }
 
-extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f64,
-                                    const uint8_t* rgb, int64_t n, double voxel,
-                                    const double* min_bound_h, int sorted, double* out_xyz,
-                                    uint8_t* out_rgb, uint32_t* out_rgb_sum, uint32_t* out_count,
-                                    int32_t* out_vox_idx, int64_t capacity, int64_t* out_m,
-                                    double* out_min_bound_h, t3d_stream stream) {
+// One K2 run.  Source = points (xyz [+ rgb]) or, when `recs` is given, partial records of other
+// ranks (then min/max bounds must be supplied).  Sink = the usual per-voxel outputs or, when
+// `part_out` is given, partial records grouped by owner (part_world owners, counts in
+// part_counts, device int32[part_world]).  max_bound_h (nullable): data maximum to size the grid
+// with (multi-GPU: the global maximum, so that every rank packs keys identically).
+static int voxel_run(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, const uint8_t* rgb,
+                     const VoxRec* recs, int recs_have_rgb, int64_t n, double voxel,
+                     const double* min_bound_h, const double* max_bound_h, int sorted, double* out_xyz,
+                     uint8_t* out_rgb, uint32_t* out_rgb_sum, uint32_t* out_count,
+                     int32_t* out_vox_idx, VoxRec* part_out, int part_world, int32_t* part_counts,
+                     int64_t capacity, int64_t* out_m, double* out_min_bound_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && out_m, "t3d_voxel_downsample: null argument");
   T3D_REQUIRE(voxel > 0.0, "t3d_voxel_downsample: voxel_size <= 0");  // Open3D raises
   cudaStream_t st = as_stream(stream);
+  if (part_out) T3D_CUDA(cudaMemsetAsync(part_counts, 0, sizeof(int32_t) * (size_t)part_world, st));
   if (n == 0) {
     T3D_CUDA(cudaMemsetAsync(out_m, 0, sizeof(int64_t), st));
     return T3D_OK;
   }
-  T3D_REQUIRE(xyz && out_xyz && n > 0, "t3d_voxel_downsample: null xyz/out_xyz");
+  T3D_REQUIRE((xyz || recs) && (out_xyz || part_out) && n > 0, "t3d_voxel_downsample: null xyz/out_xyz");
   T3D_REQUIRE(n < (1ll << 32) - 64, "t3d_voxel_downsample: more than 2^32 points in one call");
+  T3D_REQUIRE(!recs || (min_bound_h && max_bound_h), "t3d_voxel_merge_partials: bounds are required");
   T3DTrace tr("voxel_downsample");
   double mn[3], mx[3];
-  int rc = t3d_bounds(ctx, xyz, xyz_is_f64, n, mn, mx, stream);
-  if (rc != T3D_OK) return rc;
+  int rc = T3D_OK;
+  if (min_bound_h && max_bound_h) {
+    for (int c = 0; c < 3; ++c) { mn[c] = min_bound_h[c]; mx[c] = max_bound_h[c]; }
+  } else {
+    rc = t3d_bounds(ctx, xyz, xyz_is_f64, n, mn, mx, stream);
+    if (rc != T3D_OK) return rc;
+    if (max_bound_h)
+      for (int c = 0; c < 3; ++c) mx[c] = max_bound_h[c] > mx[c] ? max_bound_h[c] : mx[c];
+  }
   tr.mark("bounds+sync");
   double minb[3];
   int bits[3];
@@ -531,7 +660,7 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
       t3d_set_error("t3d_voxel_downsample: voxel_size is too small");  // Open3D's message
       return T3D_E_NUMERIC;
     }
-    if (ext / voxel >= 2097151.0 || mn[c] < minb[c]) {
+    if (ext / voxel >= 2097151.0 || (!(min_bound_h && max_bound_h) && mn[c] < minb[c])) {
       t3d_set_error("t3d_voxel_downsample: grid exceeds 2^21 voxels per axis (or min_bound > data)");
       return T3D_E_NUMERIC;
     }
@@ -573,7 +702,9 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
   const long long warps = (n + 31) / 32;
   const long long want = (warps + 7) / 8;  // 256-thread CTAs
   const int grid = (int)(want < (long long)ctx->num_sms * 16 ? want : (long long)ctx->num_sms * 16);
-  if (xyz_is_f64)
+  if (recs)
+    rec_keys_kernel<<<grid, 256, 0, st>>>(recs, n, g, tb);
+  else if (xyz_is_f64)
     voxel_keys_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), n, g, tb);
   else
     voxel_keys_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), n, g, tb);
@@ -595,12 +726,32 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
   if ((rc = ctx->scratch[8].reserve((size_t)m * sizeof(VoxAcc) + 64)) != T3D_OK) return rc;
   tb.acc = ctx->scratch[8].as<VoxAcc>();
   T3D_CUDA(cudaMemsetAsync(tb.acc, 0, (size_t)m * sizeof(VoxAcc), st));
-  if (xyz_is_f64)
+  const int has_rgb = recs ? recs_have_rgb : (rgb != nullptr);
+  if (recs)
+    rec_accum_kernel<<<grid, 256, 0, st>>>(recs, n, has_rgb, g, tb);
+  else if (xyz_is_f64)
     voxel_accum_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), rgb, n, g, tb);
   else
     voxel_accum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), rgb, n, g, tb);
   T3D_LAUNCH_CHECK();
   ctx->launches++;
+  if (part_out) {  // sink = partial records grouped by owner
+    if ((rc = ctx->scratch[3].reserve(sizeof(int) * 2 * 64)) != T3D_OK) return rc;
+    int* offs = ctx->scratch[3].as<int>();
+    int* fill = offs + 64;
+    const int pgrid = ctx->num_sms * 8;
+    if (m > 0) {
+      partials_count_kernel<<<pgrid, 256, 0, st>>>(tb, m, part_world, part_counts);
+      T3D_LAUNCH_CHECK();
+      partials_offsets_kernel<<<1, 32, 0, st>>>(part_counts, part_world, offs, fill);
+      T3D_LAUNCH_CHECK();
+      partials_scatter_kernel<<<pgrid, 256, 0, st>>>(tb, m, part_world, has_rgb, offs, fill, part_out);
+      T3D_LAUNCH_CHECK();
+      ctx->launches += 3;
+    }
+    T3D_CUDA(cudaMemcpyAsync(out_m, tb.counter, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return T3D_OK;
+  }
 
   const unsigned* order = nullptr;
   const int fgrid = ctx->num_sms * 8;
@@ -622,7 +773,7 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
     order = ids;
   }
   if (m > 0) {
-    voxel_finalize_kernel<<<fgrid, 256, 0, st>>>(tb, order, m, rgb != nullptr, out_xyz, out_rgb,
+    voxel_finalize_kernel<<<fgrid, 256, 0, st>>>(tb, order, m, has_rgb, out_xyz, out_rgb,
                                                  out_rgb_sum, out_count, out_vox_idx);
     T3D_LAUNCH_CHECK();
     ctx->launches++;
@@ -630,6 +781,41 @@ extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f6
   T3D_CUDA(cudaMemcpyAsync(out_m, tb.counter, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (tr.on) { cudaStreamSynchronize(st); tr.mark("pass2+finalize"); }
   return T3D_OK;
+}
+
+extern "C" int t3d_voxel_downsample(t3d_ctx* ctx, const void* xyz, int xyz_is_f64,
+                                    const uint8_t* rgb, int64_t n, double voxel,
+                                    const double* min_bound_h, int sorted, double* out_xyz,
+                                    uint8_t* out_rgb, uint32_t* out_rgb_sum, uint32_t* out_count,
+                                    int32_t* out_vox_idx, int64_t capacity, int64_t* out_m,
+                                    double* out_min_bound_h, t3d_stream stream) {
+  return voxel_run(ctx, xyz, xyz_is_f64, rgb, nullptr, 0, n, voxel, min_bound_h, nullptr, sorted, out_xyz, out_rgb,
+                   out_rgb_sum, out_count, out_vox_idx, nullptr, 0, nullptr, capacity, out_m, out_min_bound_h,
+                   stream);
+}
+
+extern "C" int t3d_voxel_partials(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, const uint8_t* rgb,
+                                  int64_t n, double voxel, const double* min_bound_h,
+                                  const double* max_bound_h, int world, void* out_records,
+                                  int64_t capacity, int32_t* out_counts, int64_t* out_m,
+                                  t3d_stream stream) {
+  T3D_REQUIRE(min_bound_h && max_bound_h && out_counts && world >= 1 && world <= 64 && (capacity == 0 || out_records),
+              "t3d_voxel_partials: bad argument");
+  return voxel_run(ctx, xyz, xyz_is_f64, rgb, nullptr, 0, n, voxel, min_bound_h, max_bound_h, 0, nullptr, nullptr,
+                   nullptr, nullptr, nullptr, reinterpret_cast<VoxRec*>(out_records), world, out_counts, capacity,
+                   out_m, nullptr, stream);
+}
+
+extern "C" int t3d_voxel_merge_partials(t3d_ctx* ctx, const void* records, int64_t n_records, int has_rgb,
+                                        double voxel, const double* min_bound_h,
+                                        const double* max_bound_h, int sorted, double* out_xyz,
+                                        uint8_t* out_rgb, uint32_t* out_rgb_sum, uint32_t* out_count,
+                                        int32_t* out_vox_idx, int64_t capacity, int64_t* out_m,
+                                        t3d_stream stream) {
+  T3D_REQUIRE(min_bound_h && max_bound_h && (n_records == 0 || records), "t3d_voxel_merge_partials: bad argument");
+  return voxel_run(ctx, nullptr, 0, nullptr, reinterpret_cast<const VoxRec*>(records), has_rgb, n_records, voxel,
+                   min_bound_h, max_bound_h, sorted, out_xyz, out_rgb, out_rgb_sum, out_count, out_vox_idx, nullptr, 0,
+                   nullptr, capacity, out_m, nullptr, stream);
 }
 
 extern "C" int t3d_compact_rows(t3d_ctx* ctx, const void* rows, int64_t n, int32_t row_bytes,

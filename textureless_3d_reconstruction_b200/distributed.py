@@ -337,3 +337,112 @@ def sharded_icp(ctx, src_shard, tgt, tgt_nrm, max_corr_dist, n_src_total, init=N
         if stop:
             break
     return T, fit, rmse, it
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 sharded: every rank holds a shard of the points; owner(voxel) = hash(index) mod G.
+# ---------------------------------------------------------------------------------------------------
+def sharded_voxel_downsample(ops, xyz, rgb, voxel_size, group=None, sorted_output=True):
+    """Voxel-grid downsample of the union of all ranks' points.  `ops` provides bounds(),
+    voxel_partials() and voxel_merge_partials() (runtime.Context on the GPU; a NumPy stand-in in the
+    gloo tests).  Steps: exact all_reduce of the bounds -> per-rank partial sums per voxel, grouped by
+    owner -> one all_to_all for the counts and one for the 56-byte records -> the owner adds the
+    partials and divides once.  Returns this rank's OWNED voxels (dict as voxel_downsample); the
+    union over ranks equals the single-GPU result bit for bit for float32 points."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = xyz.device
+    big = np.full(3, np.inf)
+    mn, mx = ops.bounds(xyz) if xyz.shape[0] else (big, -big)
+    b = torch.tensor(np.concatenate([mn, -np.asarray(mx)]), dtype=torch.float64, device=dev)
+    dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
+    b = b.cpu().numpy()
+    if not np.isfinite(b).all():                      # no rank has points
+        return dict(points=torch.empty((0, 3), dtype=torch.float64, device=dev), colors=None, rgb_sum=None,
+                    count=torch.empty(0, dtype=torch.int32, device=dev),
+                    idx=torch.empty((0, 3), dtype=torch.int32, device=dev), min_bound=None, m=0)
+    gmin, gmax = b[:3], -b[3:]
+    minb = gmin - voxel_size * 0.5                    # R2: min_bound = min(p) - 0.5 * v, one global grid
+    rec, counts = ops.voxel_partials(xyz, rgb, voxel_size, minb, gmax, world)
+    send_counts = counts.to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+    recv = torch.empty((sum(rc), rec.shape[1]), dtype=rec.dtype, device=dev)
+    dist.all_to_all_single(recv, rec.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
+    out = ops.voxel_merge_partials(recv, rgb is not None, voxel_size, minb, gmax, sorted_output)
+    out["records_sent"], out["records_received"] = int(sum(sc)), int(sum(rc))
+    return out
+
+
+def gather_rows(rows, dst=0, group=None):
+    """Concatenate every rank's (n_r, ...) tensor on rank `dst` in rank order (None elsewhere):
+    all_gather of the row counts + one all_to_all in which only `dst` receives."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x.item()) for x in ns]
+    flat = rows.reshape(rows.shape[0], -1).contiguous()
+    sc = [flat.shape[0] if d == dst else 0 for d in range(world)]
+    rc = ns if rank == dst else [0] * world
+    recv = torch.empty((sum(rc), flat.shape[1]), dtype=flat.dtype, device=flat.device)
+    dist.all_to_all_single(recv, flat, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return recv.reshape((-1,) + tuple(rows.shape[1:])) if rank == dst else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# K6 / K9 sharded (SURVEY 8e): each owner extracts the surface of its z-slab; the +z neighbour tests
+# and gradients at the slab's upper face need the first block layer(s) of the next slab (a halo).
+# ---------------------------------------------------------------------------------------------------
+def extract_owned_surface(vol, rank, world, slab_blocks, weight_threshold=3.0, axis=2, halo_blocks=1, group=None):
+    """Surface points (R6) of the blocks this rank owns, exactly as a single volume holding every
+    rank's blocks would emit them: the halo layers [hi, hi + halo_blocks) of the upper neighbour and
+    [lo - halo_blocks, lo) of the lower one are fetched first (block records, one all_to_all), merged
+    as read-only context, and extraction is restricted to the owned range.
+    Returns (xyz f32, normals f32, rgb u8) device tensors."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = block_owner_range(rank, world, slab_blocks)
+    lo_c, hi_c = max(lo, -(1 << 20)), min(hi, 1 << 20)
+    # what the neighbours need from me: my lowest layers go down, my highest layers go up
+    send = []
+    for d in range(world):
+        if d == rank - 1:
+            send.append(vol.export_blocks_range(axis, lo_c, lo_c + halo_blocks))
+        elif d == rank + 1:
+            send.append(vol.export_blocks_range(axis, hi_c - halo_blocks, hi_c))
+        else:
+            send.append(None)
+    dev = vol.ctx.device if hasattr(vol, "ctx") else "cpu"
+    sc = torch.tensor([0 if s_ is None else s_[0].shape[0] for s_ in send], dtype=torch.int64, device=dev)
+    rcv = torch.empty_like(sc)
+    dist.all_to_all_single(rcv, sc, group=group)
+    scl, rcl = sc.cpu().tolist(), rcv.cpu().tolist()
+
+    def cat(i, shape, dtype):
+        parts = [s_[i].reshape((s_[i].shape[0],) + shape) for s_ in send if s_ is not None and s_[0].shape[0]]
+        return torch.cat(parts).contiguous() if parts else torch.empty((0,) + shape, dtype=dtype, device=dev)
+    out = []
+    for i, (shape, dtype) in enumerate([((3,), torch.int32), ((512,), torch.float32), ((512,), torch.float32),
+                                        ((512, 3), torch.float32)]):
+        snd = cat(i, shape, dtype)
+        flat = snd.reshape(snd.shape[0], -1)
+        r = torch.empty((sum(rcl), flat.shape[1]), dtype=dtype, device=dev)
+        dist.all_to_all_single(r, flat, output_split_sizes=rcl, input_split_sizes=scl, group=group)
+        out.append(r.reshape((-1,) + shape))
+    # a scratch volume = exact copy of the owned slab + the neighbours' halo layers: the fused volume
+    # is not modified, and this rank's own partial copies of non-owned blocks stay out of the picture
+    own = vol.export_blocks_range(axis, lo_c, hi_c)
+    tmp = type(vol)(vol.voxel_size, vol.sdf_trunc, block_capacity=max(2 * (own[0].shape[0] + out[0].shape[0]), 1024),
+                    ctx=vol.ctx)
+    if own[0].shape[0]:
+        tmp.merge_blocks(*[t.contiguous() for t in own])
+    if out[0].shape[0]:
+        tmp.merge_blocks(out[0].contiguous(), out[1].contiguous(), out[2].contiguous(), out[3].contiguous())
+    res = tmp.extract_points_range(axis, lo_c, hi_c, weight_threshold)
+    tmp.close()
+    return res

@@ -190,6 +190,49 @@ class Context:
                     rgb_sum=None if o_sum is None else o_sum[:m], count=o_cnt[:m],
                     idx=None if o_idx is None else o_idx[:m], min_bound=mb_out, m=m)
 
+    VOXEL_RECORD_BYTES = 56
+
+    def voxel_partials(self, xyz, rgb, voxel_size, min_bound, max_bound, world):
+        """Sharded K2, sender side: (records uint8[M,56] grouped by owner, counts int32[world]) on the
+        device.  min_bound / max_bound: the GLOBAL grid origin (min - voxel/2) and data maximum."""
+        torch = _torch()
+        n = xyz.shape[0]
+        dev = xyz.device
+        rec = torch.empty((max(n, 1), self.VOXEL_RECORD_BYTES), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(world, dtype=torch.int32, device=dev)
+        o_m = torch.zeros(1, dtype=torch.int64, device=dev)
+        mb = np.ascontiguousarray(min_bound, np.float64)
+        xb = np.ascontiguousarray(max_bound, np.float64)
+        check(self.lib.t3d_voxel_partials(self.handle, _ptr(xyz), int(xyz.dtype == torch.float64), _ptr(rgb), n,
+                                          float(voxel_size), _np_ptr(mb), _np_ptr(xb), int(world), _ptr(rec),
+                                          rec.shape[0], _ptr(cnt), _ptr(o_m), _stream()))
+        return rec[: int(o_m.item())], cnt
+
+    def voxel_merge_partials(self, records, has_rgb, voxel_size, min_bound, max_bound, sorted_output=True):
+        """Sharded K2, owner side: merge the records received from every rank; same outputs as
+        voxel_downsample."""
+        torch = _torch()
+        n = records.shape[0]
+        dev = records.device
+        assert records.dtype == torch.uint8 and records.is_contiguous()
+        cap = max(n, 1)
+        o_xyz = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+        o_rgb = torch.empty((cap, 3), dtype=torch.uint8, device=dev) if has_rgb else None
+        o_sum = torch.empty((cap, 3), dtype=torch.int32, device=dev) if has_rgb else None
+        o_cnt = torch.empty(cap, dtype=torch.int32, device=dev)
+        o_idx = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+        o_m = torch.zeros(1, dtype=torch.int64, device=dev)
+        mb = np.ascontiguousarray(min_bound, np.float64)
+        xb = np.ascontiguousarray(max_bound, np.float64)
+        check(self.lib.t3d_voxel_merge_partials(self.handle, _ptr(records), n, int(bool(has_rgb)), float(voxel_size),
+                                                _np_ptr(mb), _np_ptr(xb), int(bool(sorted_output)), _ptr(o_xyz),
+                                                _ptr(o_rgb), _ptr(o_sum), _ptr(o_cnt), _ptr(o_idx), cap, _ptr(o_m),
+                                                _stream()))
+        m = int(o_m.item())
+        return dict(points=o_xyz[:m], colors=None if o_rgb is None else o_rgb[:m],
+                    rgb_sum=None if o_sum is None else o_sum[:m], count=o_cnt[:m], idx=o_idx[:m],
+                    min_bound=mb, m=m)
+
     def bounds(self, xyz):
         torch = _torch()
         mn, mx = np.zeros(3), np.zeros(3)
@@ -606,6 +649,24 @@ class TSDFVolume:
                 return xyz[:cnt], (nrm[:cnt] if nrm is not None else None), (rgb[:cnt] if rgb is not None else None)
             cap = cnt
 
+
+    def extract_points_range(self, axis, lo, hi, weight_threshold=3.0, with_normals=True, with_colors=True):
+        """K6 over the blocks with key[axis] in [lo, hi) only (the owned slab of a sharded volume)."""
+        torch = _torch()
+        dev = self.ctx.device
+        cap = max(self.count_blocks_range(axis, lo, hi) * 96, 1024)
+        while True:
+            xyz = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            nrm = torch.empty((cap, 3), dtype=torch.float32, device=dev) if with_normals else None
+            rgb = torch.empty((cap, 3), dtype=torch.uint8, device=dev) if with_colors else None
+            n = torch.zeros(1, dtype=torch.int64, device=dev)
+            check(self.lib.t3d_tsdf_extract_points_range(self.handle, int(axis), int(lo), int(hi),
+                                                         float(weight_threshold), _ptr(xyz), _ptr(nrm), _ptr(rgb), cap,
+                                                         _ptr(n), _stream()))
+            cnt = int(n.item())
+            if cnt <= cap:
+                return xyz[:cnt], (nrm[:cnt] if nrm is not None else None), (rgb[:cnt] if rgb is not None else None)
+            cap = cnt
 
     def extract_mesh(self, weight_threshold=3.0, with_normals=True, with_colors=True):
         """K10: marching-cubes triangle mesh of the fused surface (Open3D extract_triangle_mesh
