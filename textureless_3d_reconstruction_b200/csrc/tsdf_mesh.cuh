@@ -28,29 +28,6 @@ struct MeshOut {
   int* tbase;                  // per block
 };
 
-// exclusive scan of one int per thread over a 256-thread CTA; returns the exclusive prefix and the total
-__device__ __forceinline__ int cta_scan256(int x, int* s_warp, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = x;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  __syncthreads();  // s_warp reuse
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  int base = 0, tot = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const int c = s_warp[w];
-    if (w < warp) base += c;
-    tot += c;
-  }
-  *total = tot;
-  return base + inc - x;
-}
-
 constexpr int CV = 9;  // cube bases -1..7 per axis
 
 __global__ void __launch_bounds__(256)
