@@ -398,6 +398,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
   __shared__ __align__(8) uint64_t s_dfull[ST_DSLOTS];
   __shared__ __align__(8) uint64_t s_cfull[ST_CSLOTS];
   __shared__ int s_tiles[ST_DSLOTS];
+  __shared__ int s_fi[ST_DSLOTS];
+  __shared__ int s_ltile[ST_DSLOTS];
   __shared__ int s_wcount[2 * BP_WARPS];
   __shared__ int s_woff[ST_DSLOTS][2 * BP_WARPS];
   __shared__ int s_total[ST_DSLOTS];
@@ -418,6 +420,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
     s_tiles[ds] = tile;
     const int fi = tile / p.tiles_per_frame;
     const int ltile = tile - fi * p.tiles_per_frame;
+    s_fi[ds] = fi;          // one division per tile instead of one per thread and use
+    s_ltile[ds] = ltile;
     if (p.P - ltile * ST_TILE < ST_TILE) return;
     mbar_expect_tx(&s_dfull[ds], ST_DEPTH_BYTES);
     tma_bulk_g2s(s_depth + ds * ST_DEPTH_BYTES,
@@ -456,8 +460,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
     excl_out = 0;
     const int tile = s_tiles[ds];
     if (tile < 0) return;  // uniform
-    const int fi = tile / p.tiles_per_frame;
-    const int ltile = tile - fi * p.tiles_per_frame;
+    const int fi = s_fi[ds];
+    const int ltile = s_ltile[ds];
     const BPFrame& fr = p.f[fi];
     const int npx = min(ST_TILE, p.P - ltile * ST_TILE);
     const float* sd = reinterpret_cast<const float*>(s_depth + ds * ST_DEPTH_BYTES);
@@ -471,6 +475,25 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
       __syncthreads();
     }
     unsigned m = 0;
+    if (npx == ST_TILE && fr.conf == nullptr) {  // the common case: no per-pixel bounds / mask tests
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float4 a = *reinterpret_cast<const float4*>(sd + g * (ST_TILE / 2) + 4 * tid);
+        const float d32[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bool valid;
+          if (!F64_MASK) {
+            const float ds_ = __fmul_rn(d32[k], p.scale32);
+            valid = (ds_ > p.min32) && (ds_ < p.max32);
+          } else {
+            const double ds_ = __dmul_rn((double)d32[k], p.scale);
+            valid = (ds_ > p.min_d) && (ds_ < p.max_d);
+          }
+          if (valid) m |= 1u << (4 * g + k);
+        }
+      }
+    } else
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int idx = g * (ST_TILE / 2) + 4 * tid;
@@ -580,8 +603,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
     const int cs = it % ST_CSLOTS;
     const int tile = s_tiles[ds];
     if (tile < 0) break;  // tickets are monotonic: the other slots hold nothing either
-    const int fi = tile / p.tiles_per_frame;
-    const int ltile = tile - fi * p.tiles_per_frame;
+    const int fi = s_fi[ds];
+    const int ltile = s_ltile[ds];
     const BPFrame& fr = p.f[fi];
     const int npx = min(ST_TILE, p.P - ltile * ST_TILE);
     const uint8_t* sd = s_depth + ds * ST_DEPTH_BYTES;
