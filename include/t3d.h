@@ -173,6 +173,19 @@ int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t n, int nb,
                             uint8_t* keep_mask, int64_t* out_kept,
                             double* stats_h, t3d_stream stream);
 
+/* Sharded K3 (replicate the — small, downsampled — cloud, shard the queries).
+ * t3d_sor_mean_distances_part: mean distance to the nb nearest neighbours for the points at
+ *   grid-sorted positions [part*n/parts, (part+1)*n/parts) only; other entries of out_mean_dist
+ *   (n doubles, indexed like xyz) stay untouched — initialise to -inf and all_reduce(MAX) the
+ *   ranks' vectors.  The grid order is a stable sort of the full cloud, identical on every rank.
+ * t3d_sor_from_mean_distances: mu, sigma, threshold and keep mask from a complete vector
+ *   (stats_h: host double[3] = mu, sigma, threshold; nullable).  Both synchronous. */
+int t3d_sor_mean_distances_part(t3d_ctx* ctx, const double* xyz, int64_t n, int nb, int part,
+                                int parts, double* out_mean_dist, t3d_stream stream);
+int t3d_sor_from_mean_distances(t3d_ctx* ctx, const double* mean_dist, int64_t n,
+                                double std_ratio, uint8_t* keep_mask, int64_t* out_kept,
+                                double* stats_h, t3d_stream stream);
+
 /* Ordered compaction of rows by a byte mask (keeps input order, R3). */
 int t3d_compact_rows(t3d_ctx* ctx, const void* rows, int64_t n,
                      int32_t row_bytes, const uint8_t* keep_mask,

@@ -1,5 +1,7 @@
 """2+ GPU check (torchrun) of the sharded cloud path:
   * sharded_voxel_downsample over per-rank shards == one voxel_downsample over all points (bit-identical),
+  * sharded_statistical_outlier (queries split over the ranks, all_reduce(MAX) of the mean distances) ==
+    one statistical_outlier call (bit-identical means, same mask),
   * extract_owned_surface (halo exchange + range-restricted K6) of a z-sharded, routed volume ==
     the surface points of one volume that fused every rank's frames, gathered to rank 0 and written
     as one .ply.
@@ -85,11 +87,18 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             write_ply(Path(td) / "fused.ply", gp, g_rgb.cpu().numpy(), g_nrm.cpu().numpy())
             ok_k6 = ok_k6 and (Path(td) / "fused.ply").stat().st_size > len(gp) * 51
-    res = torch.tensor([int(ok_k2), int(ok_k6)], device="cuda")
+    # ---- K3 sharded: the (replicated) downsampled cloud, queries split over the ranks
+    full = ctx.voxel_downsample(torch.from_numpy(p[:200_000]).cuda(), None, 0.05)["points"].contiguous()
+    keep, mean, stats, kept = D.sharded_statistical_outlier(ctx, full, 20, 2.0)
+    keep1, mean1, stats1, kept1 = ctx.statistical_outlier(full, 20, 2.0)
+    ok_k3 = (torch.equal(mean.view(torch.int64), mean1.view(torch.int64)) and torch.equal(keep, keep1)
+             and stats == stats1 and kept == kept1 and 0 < kept < full.shape[0])
+    res = torch.tensor([int(ok_k2), int(ok_k6), int(ok_k3)], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"MGPU_CLOUD_CHECK sharded_k2==single {bool(res[0].item())} owned_surface==serial {bool(res[1].item())} "
-              f"voxels={allrows.shape[0]} {info}", flush=True)
+              f"sharded_k3==single {bool(res[2].item())} voxels={allrows.shape[0]} {info} sor_kept={kept}/{full.shape[0]}",
+              flush=True)
     router.close()
     dist.destroy_process_group()
     sys.exit(0 if res.min().item() == 1 else 1)

@@ -283,3 +283,25 @@ def test_voxel_partials_then_merge_equals_downsample(ctx, world):
     assert np.array_equal(cnt[order], ref["count"].cpu().numpy())
     # every owner holds only its own voxels, each voxel exactly once
     assert len(np.unique(idx, axis=0)) == len(idx)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 5])
+def test_sor_parts_tile_the_cloud_and_equal_the_single_call(ctx, parts):
+    """Sharded K3 building blocks on one GPU: the `parts` shares of the grid-sorted cloud cover every
+    point exactly once, and mean distances / mu / sigma / mask equal t3d_statistical_outlier's."""
+    import torch
+    pts, _ = cloud(2)
+    ds = ctx.voxel_downsample(torch.from_numpy(pts).cuda(), None, 0.01)["points"].contiguous()
+    n = ds.shape[0]
+    keep0, mean0, stats0, kept0 = ctx.statistical_outlier(ds, 20, 2.0)
+    acc = torch.full((n,), float("-inf"), dtype=torch.float64, device=ds.device)
+    covered = torch.zeros(n, dtype=torch.int32, device=ds.device)
+    for r in range(parts):
+        part = torch.full((n,), float("-inf"), dtype=torch.float64, device=ds.device)
+        ctx.sor_mean_distances_part(ds, 20, r, parts, part)
+        covered += torch.isfinite(part).to(torch.int32)
+        acc = torch.maximum(acc, part)                              # what all_reduce(MAX) does
+    assert int(covered.min()) == 1 and int(covered.max()) == 1
+    assert torch.equal(acc.view(torch.int64), mean0.view(torch.int64))       # bit-identical mean distances
+    keep, stats, kept = ctx.sor_from_mean_distances(acc, 2.0)
+    assert stats == stats0 and kept == kept0 and torch.equal(keep, keep0)

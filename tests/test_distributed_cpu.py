@@ -258,3 +258,68 @@ def test_sharded_voxel_downsample_world2(oracle):
     ref0 = oracle.voxel_downsample(p[cut[0]:cut[1]].astype(np.float64), c[cut[0]:cut[1]], 0.05)
     assert res[0][3] + res[1][3] == len(ref0["points"])
     assert res[0][4] > 0
+
+
+class NumpySorOps:
+    """CPU stand-in for the two sharded-K3 calls: brute-force kNN for this part of the (index-ordered)
+    cloud; R3's mu / sigma / threshold from the complete vector."""
+
+    @staticmethod
+    def sor_mean_distances_part(xyz, nb, part, parts, out_mean):
+        p = xyz.numpy()
+        n = len(p)
+        lo, hi = n * part // parts, n * (part + 1) // parts
+        d = np.sqrt(((p[lo:hi, None, :] - p[None, :, :]) ** 2).sum(-1))
+        d.sort(axis=1)
+        out_mean[lo:hi] = torch.from_numpy(d[:, :nb].mean(1))
+        return out_mean
+
+    @staticmethod
+    def sor_from_mean_distances(mean, std_ratio):
+        m = mean.numpy()
+        mu = m.sum() / len(m)
+        sigma = np.sqrt(((m - mu) ** 2).sum() / (len(m) - 1))
+        thr = mu + std_ratio * sigma
+        keep = (m > 0) & (m < thr)
+        return torch.from_numpy(keep.astype(np.uint8)), (mu, sigma, thr), int(keep.sum())
+
+
+def _sor_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(9)
+        pts = rng.uniform(0, 1, (600, 3))
+        pts[:5] += 3.0                                     # outliers
+        keep, mean, stats, kept = D.sharded_statistical_outlier(NumpySorOps, torch.from_numpy(pts), 20, 2.0)
+        q.put((rank, keep.numpy(), mean.numpy(), stats, kept))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_statistical_outlier_world2(oracle):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sor_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(0, 1, (600, 3))
+    pts[:5] += 3.0
+    ref = oracle.statistical_outlier(pts, 20, 2.0)
+    for r in range(world):
+        assert np.isfinite(res[r][2]).all()                                  # every query was owned by some rank
+        assert np.array_equal(res[r][1], res[0][1]) and res[r][4] == res[0][4]
+    ref_keep = ref["keep"] if isinstance(ref, dict) else ref[0]
+    assert np.array_equal(res[0][1].astype(bool), np.asarray(ref_keep).astype(bool))
+    assert not res[0][1][:5].any()

@@ -78,6 +78,8 @@ _SIGS = {
     "t3d_voxel_merge_partials": (_I, [_VP, _VP, _I64, _I, _D, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "t3d_bounds": (_I, [_VP, _VP, _I, _I64, _VP, _VP, _VP]),
     "t3d_statistical_outlier": (_I, [_VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),
+    "t3d_sor_mean_distances_part": (_I, [_VP, _VP, _I64, _I, _I, _I, _VP, _VP]),
+    "t3d_sor_from_mean_distances": (_I, [_VP, _VP, _I64, _D, _VP, _VP, _VP, _VP]),
     "t3d_compact_rows": (_I, [_VP, _VP, _I64, C.c_int32, _VP, _VP, _VP, _VP]),
     "t3d_tsdf_create": (_I, [_VP, C.POINTER(TsdfParams), C.POINTER(_VP)]),
     "t3d_tsdf_destroy": (None, [_VP]),

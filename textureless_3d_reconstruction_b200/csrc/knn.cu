@@ -278,9 +278,11 @@ inline size_t knn_smem_bytes(int k) { return (size_t)k * KNN_THREADS * (sizeof(d
 
 // K3: mean distance to the nb nearest neighbours (self included), R3.
 __global__ void __launch_bounds__(128)
-    sor_mean_kernel(const __grid_constant__ GridDev g, int nb, double* mean_dist) {
+    sor_mean_kernel(const __grid_constant__ GridDev g, int nb, double* mean_dist, long long lo, long long hi) {
+  // [lo, hi): range of GRID-SORTED positions handled by this launch (multi-GPU: a rank's share;
+  // contiguous in cell order, so every warp stays fully busy)
   const double* pts = reinterpret_cast<const double*>(g.sorted_xyz);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi;
        i += (long long)gridDim.x * blockDim.x) {
     double* bd;
     unsigned* bi;
@@ -459,6 +461,9 @@ __global__ void __launch_bounds__(128)
 }
 }  // namespace
 
+static int sor_from_means(t3d_ctx* ctx, const double* mean, int64_t n, double std_ratio, uint8_t* keep_mask,
+                          int64_t* out_kept, double* stats_h, cudaStream_t st);
+
 extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t n, int nb,
                                        double std_ratio, double* out_mean_dist,
                                        uint8_t* keep_mask, int64_t* out_kept, double* stats_h,
@@ -481,8 +486,16 @@ extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t 
   }
   const long long want = (n + 127) / 128;
   const int mgrid = (int)(want < 2ll * grid ? want : 2ll * grid);
-  sor_mean_kernel<<<mgrid, KNN_THREADS, knn_smem_bytes(nb), st>>>(g, nb, mean);
+  sor_mean_kernel<<<mgrid, KNN_THREADS, knn_smem_bytes(nb), st>>>(g, nb, mean, 0, n);
   T3D_LAUNCH_CHECK();
+  return sor_from_means(ctx, mean, n, std_ratio, keep_mask, out_kept, stats_h, st);
+}
+
+// R3 steps 2-4 from the per-point mean distances: mu, sigma (Bessel), threshold, keep mask.
+static int sor_from_means(t3d_ctx* ctx, const double* mean, int64_t n, double std_ratio, uint8_t* keep_mask,
+                          int64_t* out_kept, double* stats_h, cudaStream_t st) {
+  int rc;
+  const int grid = ctx->num_sms * 8;
   // mu, sigma: per-CTA partials summed on the host in a fixed order
   const int sgrid = 256;
   if ((rc = ctx->scratch[7].reserve(sizeof(double) * 2 * sgrid)) != T3D_OK) return rc;
@@ -516,6 +529,45 @@ extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t 
   ctx->launches += 2;
   T3D_CUDA(cudaStreamSynchronize(st));
   return T3D_OK;
+}
+
+// Sharded K3 (replicate the cloud, shard the queries).  Mean neighbour distance of the
+// points at grid-sorted positions [part * n / parts, (part + 1) * n / parts) only; the other
+// entries of out_mean_dist are left untouched (callers initialise them to -inf and combine the
+// ranks' vectors with an all_reduce(MAX)).  The grid is built from the full cloud with a stable
+// sort, so every rank sees the same order and the parts tile the cloud exactly.
+extern "C" int t3d_sor_mean_distances_part(t3d_ctx* ctx, const double* xyz, int64_t n, int nb, int part,
+                                           int parts, double* out_mean_dist, t3d_stream stream) {
+  T3D_REQUIRE(ctx && out_mean_dist && parts >= 1 && part >= 0 && part < parts, "t3d_sor_mean_distances_part: bad argument");
+  T3D_REQUIRE(nb >= 1 && nb <= KMAX, "t3d_sor_mean_distances_part: nb_neighbors must be in [1,%d]", KMAX);
+  if (n == 0) return T3D_OK;
+  T3D_REQUIRE(xyz, "t3d_sor_mean_distances_part: null xyz");
+  cudaStream_t st = as_stream(stream);
+  GridDev g;
+  int rc = t3d_grid_build(ctx, xyz, 1, n, -1.0, &g, st, nb);
+  if (rc != T3D_OK) return rc;
+  const long long lo = (long long)n * part / parts, hi = (long long)n * (part + 1) / parts;
+  if (hi > lo) {
+    const long long want = (hi - lo + 127) / 128;
+    const long long cap = 2ll * ctx->num_sms * 8;
+    sor_mean_kernel<<<(int)(want < cap ? want : cap), KNN_THREADS, knn_smem_bytes(nb), st>>>(g, nb, out_mean_dist, lo, hi);
+    T3D_LAUNCH_CHECK();
+    ctx->launches++;
+  }
+  T3D_CUDA(cudaStreamSynchronize(st));
+  return T3D_OK;
+}
+
+// The rest of R3 from a complete vector of mean distances (all ranks hold the same one).
+extern "C" int t3d_sor_from_mean_distances(t3d_ctx* ctx, const double* mean_dist, int64_t n, double std_ratio,
+                                           uint8_t* keep_mask, int64_t* out_kept, double* stats_h,
+                                           t3d_stream stream) {
+  T3D_REQUIRE(ctx && keep_mask && out_kept && std_ratio > 0.0, "t3d_sor_from_mean_distances: bad argument");
+  cudaStream_t st = as_stream(stream);
+  T3D_CUDA(cudaMemsetAsync(out_kept, 0, sizeof(int64_t), st));
+  if (n == 0) return T3D_OK;
+  T3D_REQUIRE(mean_dist, "t3d_sor_from_mean_distances: null mean_dist");
+  return sor_from_means(ctx, mean_dist, n, std_ratio, keep_mask, out_kept, stats_h, st);
 }
 
 extern "C" int t3d_estimate_normals(t3d_ctx* ctx, const float* xyz, int64_t n, int knn,

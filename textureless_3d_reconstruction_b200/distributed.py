@@ -376,6 +376,22 @@ def sharded_voxel_downsample(ops, xyz, rgb, voxel_size, group=None, sorted_outpu
     return out
 
 
+def sharded_statistical_outlier(ops, xyz, nb_neighbors=20, std_ratio=2.0, group=None):
+    """remove_statistical_outlier (R3) with the kNN queries sharded over the ranks.  `xyz`
+    is the FULL cloud, replicated on every rank (it is the downsampled one: small); rank r computes
+    the mean neighbour distance for its share of the grid-sorted points, one all_reduce(MAX) over a
+    -inf-initialised vector assembles them, and every rank derives the same mu / sigma / mask.
+    Returns (keep u8[N], mean f64[N], (mu, sigma, thr), kept) — identical to the single-GPU call."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mean = torch.full((xyz.shape[0],), float("-inf"), dtype=torch.float64, device=xyz.device)
+    ops.sor_mean_distances_part(xyz, nb_neighbors, rank, world, mean)
+    dist.all_reduce(mean, op=dist.ReduceOp.MAX, group=group)
+    keep, stats, kept = ops.sor_from_mean_distances(mean, std_ratio)
+    return keep, mean, stats, kept
+
+
 def gather_rows(rows, dst=0, group=None):
     """Concatenate every rank's (n_r, ...) tensor on rank `dst` in rank order (None elsewhere):
     all_gather of the row counts + one all_to_all in which only `dst` receives."""

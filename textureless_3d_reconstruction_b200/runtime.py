@@ -254,6 +254,25 @@ class Context:
                                                _ptr(mean), _ptr(keep), _ptr(kept), _np_ptr(stats), _stream()))
         return keep[:n], mean[:n], tuple(stats), int(kept.item())
 
+    def sor_mean_distances_part(self, xyz, nb_neighbors, part, parts, out_mean):
+        """Sharded K3, query side: fill out_mean (f64[N]) for this part's share of the cloud."""
+        torch = _torch()
+        assert xyz.dtype == torch.float64 and xyz.is_contiguous() and out_mean.dtype == torch.float64
+        check(self.lib.t3d_sor_mean_distances_part(self.handle, _ptr(xyz), xyz.shape[0], int(nb_neighbors), int(part),
+                                                   int(parts), _ptr(out_mean), _stream()))
+        return out_mean
+
+    def sor_from_mean_distances(self, mean, std_ratio=2.0):
+        """Sharded K3, after the all_reduce: (keep u8[N], (mu, sigma, thr), kept)."""
+        torch = _torch()
+        n = mean.shape[0]
+        keep = torch.zeros(max(n, 1), dtype=torch.uint8, device=mean.device)
+        kept = torch.zeros(1, dtype=torch.int64, device=mean.device)
+        stats = np.zeros(3, np.float64)
+        check(self.lib.t3d_sor_from_mean_distances(self.handle, _ptr(mean), n, float(std_ratio), _ptr(keep), _ptr(kept),
+                                                   _np_ptr(stats), _stream()))
+        return keep[:n], tuple(stats), int(kept.item())
+
     def compact_rows(self, rows, keep):
         torch = _torch()
         n = rows.shape[0]
