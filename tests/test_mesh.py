@@ -171,6 +171,8 @@ def test_gpu_mesh_matches_oracle_on_analytic_fields(ctx, oracle, field, lo, hi):
     vol = gpu_volume(ctx, blocks)
     for thr in (3.0, 5.0, 6.0):
         assert_same_mesh(vol.extract_mesh(thr), ov.extract_mesh(thr))
+    # a capacity guess that is too small triggers the exactly-sized second pass
+    assert_same_mesh(vol.extract_mesh(3.0, capacity=(10, 7)), ov.extract_mesh(3.0))
     # without optional attributes
     x, n, c, t = vol.extract_mesh(3.0, with_normals=False, with_colors=False)
     assert n is None and c is None and len(t) == len(ov.extract_mesh(3.0)[3])

@@ -687,27 +687,32 @@ class TSDFVolume:
                 return xyz[:cnt], (nrm[:cnt] if nrm is not None else None), (rgb[:cnt] if rgb is not None else None)
             cap = cnt
 
-    def extract_mesh(self, weight_threshold=3.0, with_normals=True, with_colors=True):
+    def extract_mesh(self, weight_threshold=3.0, with_normals=True, with_colors=True, capacity=None):
         """K10: marching-cubes triangle mesh of the fused surface (Open3D extract_triangle_mesh
         semantics).  Returns (vertices f32 Vx3, normals f32 Vx3|None, colours u8 Vx3|None,
-        triangles i32 Tx3) on the device.  Two passes: count, then fill exactly-sized buffers."""
+        triangles i32 Tx3) on the device.  One pass into buffers sized from the block count
+        (capacity = (vertices, triangles) overrides the guess); a second, exactly sized pass only if
+        the guess was too small."""
         torch = _torch()
         dev = self.ctx.device
+        nb = self.num_blocks
+        vcap, tcap = capacity if capacity else (max(nb * 96, 1024), max(nb * 192, 1024))
         n = torch.zeros(2, dtype=torch.int64, device=dev)
-        check(self.lib.t3d_tsdf_extract_mesh(self.handle, float(weight_threshold), None, None, None, 0, None, 0,
-                                             _ptr(n), _stream()))
-        nv, nt = (int(x) for x in n.tolist())
-        if nv >= 2**31 - 1 or nt >= 2**31 - 1:
-            raise T3DError(-1, f"mesh too large for 32-bit indices: {nv} vertices, {nt} triangles")
-        xyz = torch.empty((nv, 3), dtype=torch.float32, device=dev)
-        nrm = torch.empty((nv, 3), dtype=torch.float32, device=dev) if with_normals else None
-        rgb = torch.empty((nv, 3), dtype=torch.uint8, device=dev) if with_colors else None
-        tri = torch.empty((nt, 3), dtype=torch.int32, device=dev)
-        if nv == 0:
-            return xyz, nrm, rgb, tri
-        check(self.lib.t3d_tsdf_extract_mesh(self.handle, float(weight_threshold), _ptr(xyz), _ptr(nrm), _ptr(rgb),
-                                             nv, _ptr(tri), nt, _ptr(n), _stream()))
-        return xyz, nrm, rgb, tri
+        while True:
+            vcap, tcap = min(int(vcap), 2**31 - 2), min(int(tcap), 2**31 - 2)
+            xyz = torch.empty((vcap, 3), dtype=torch.float32, device=dev)
+            nrm = torch.empty((vcap, 3), dtype=torch.float32, device=dev) if with_normals else None
+            rgb = torch.empty((vcap, 3), dtype=torch.uint8, device=dev) if with_colors else None
+            tri = torch.empty((tcap, 3), dtype=torch.int32, device=dev)
+            check(self.lib.t3d_tsdf_extract_mesh(self.handle, float(weight_threshold), _ptr(xyz), _ptr(nrm), _ptr(rgb),
+                                                 vcap, _ptr(tri), tcap, _ptr(n), _stream()))
+            nv, nt = (int(x) for x in n.tolist())
+            if nv >= 2**31 - 2 or nt >= 2**31 - 2:
+                raise T3DError(-1, f"mesh too large for 32-bit indices: {nv} vertices, {nt} triangles")
+            if nv <= vcap and nt <= tcap:
+                return (xyz[:nv], nrm[:nv] if nrm is not None else None, rgb[:nv] if rgb is not None else None,
+                        tri[:nt])
+            vcap, tcap = max(nv, 1), max(nt, 1)
 
     def extract_points_view_async(self, K, T_cw, H, W, depth_max, weight_threshold, buffers, with_normals=True,
                                   with_colors=False):
