@@ -104,3 +104,30 @@ def test_der_cli_tracks_and_writes_ply(ctx, tmp_path, capsys):
     with pytest.raises(SystemExit) as e:
         der.main(["--input", str(empty), "--output", str(tmp_path / "o2")])
     assert e.value.code == 1
+
+
+def test_to_host_paths_agree(ctx):
+    """The host-array return path: pinned-backed results, the staged pageable path past the limit and
+    tensor.cpu() give identical arrays; pinned bytes are released when the arrays die."""
+    import gc
+    import torch
+    from textureless_3d_reconstruction_b200 import runtime as R
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape, dt in [((700_001, 3), torch.float64), ((3_000_000, 3), torch.uint8), ((10, 3), torch.float32),
+                      ((0, 3), torch.float32)]:
+        t = (torch.rand(shape, generator=g, device="cuda") * 255).to(dt)
+        ref = t.cpu().numpy()
+        base = R._pinned_out[0]
+        a = R.to_host(t)
+        assert a.dtype == ref.dtype and a.shape == ref.shape and np.array_equal(a, ref)
+        a[...] = 0                                          # the caller owns it: writable
+        old = R.PINNED_RESULT_LIMIT
+        try:
+            R.PINNED_RESULT_LIMIT = 0
+            b = R.to_host(t, chunk_bytes=1 << 20)           # staged path, several chunks
+        finally:
+            R.PINNED_RESULT_LIMIT = old
+        assert np.array_equal(b, ref)
+        del a, b
+        gc.collect()
+        assert R._pinned_out[0] == base

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from .depth_to_reconstruction import DepthImageLoader
-from .runtime import TSDFVolume, get_context, write_ply
+from .runtime import TSDFVolume, get_context, to_host, write_ply
 
 
 @dataclass
@@ -71,7 +71,7 @@ class DensePointCloudGenerator:
         xyz, rgb = self.depth_to_pointcloud_device(
             torch.from_numpy(d).to(dev), torch.from_numpy(np.ascontiguousarray(color, np.uint8)).to(dev),
             pose=pose, min_depth=min_depth, max_depth=max_depth, subsample=subsample)
-        return xyz.cpu().numpy(), rgb.cpu().numpy()
+        return to_host(xyz), to_host(rgb)
 
     def merge_pointclouds(self, pointclouds: List[Tuple[np.ndarray, np.ndarray]],
                           voxel_size: float = 0.01) -> Tuple[np.ndarray, np.ndarray]:
@@ -87,7 +87,7 @@ class DensePointCloudGenerator:
             ds = self.ctx.voxel_downsample(torch.from_numpy(np.ascontiguousarray(points)).to(dev),
                                            torch.from_numpy(np.ascontiguousarray(colors, np.uint8)).to(dev),
                                            voxel_size, sorted_output=True, want_idx=False)
-            points, colors = ds["points"].cpu().numpy(), ds["colors"].cpu().numpy()
+            points, colors = to_host(ds["points"]), to_host(ds["colors"])
         return points, colors
 
 
@@ -199,7 +199,7 @@ class DepthEnhancedReconstruction:
             self.camera_poses.append((T_cw[:3, :3].copy(), T_cw[:3, 3:4].copy()))
         self.tracker = tracker
         pts, _, cols = vol.extract_points(weight_threshold=1.0, with_normals=False)
-        all_points, all_colors = pts.cpu().numpy(), cols.cpu().numpy()
+        all_points, all_colors = to_host(pts), to_host(cols)
         self.volume = vol
         print("\n" + "=" * 70)
         print("RECONSTRUCTION COMPLETE")

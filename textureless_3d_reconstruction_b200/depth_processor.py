@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .runtime import get_context, write_ply
+from .runtime import get_context, to_host, write_ply
 
 
 @dataclass
@@ -82,7 +82,7 @@ class PointCloudGenerator:
             d = d.astype(np.float32)
         c = None if rgb is None else torch.from_numpy(np.ascontiguousarray(rgb, np.uint8)).to(dev)
         xyz, cols = self.generate_device(torch.from_numpy(d).to(dev), c, max_depth, min_depth)
-        return xyz.cpu().numpy(), (None if cols is None else cols.cpu().numpy())
+        return to_host(xyz), to_host(cols)
 
     def save_ply(self, filepath: str, points: np.ndarray, colors: Optional[np.ndarray] = None):
         """dp:424-440 — Open3D layout; colours arrive as floats in [0,1] here."""
@@ -104,7 +104,7 @@ class PointCloudGenerator:
         p = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev) if host else points.contiguous()
         c = torch.from_numpy(np.ascontiguousarray(colors, np.float32)).to(dev) if host else colors.contiguous()
         rec = self.ctx.pack_pointcloud2(p, c)
-        return rec.cpu().numpy() if host else rec
+        return to_host(rec) if host else rec
 
     def save_pcd(self, filepath: str, points: np.ndarray, colors: Optional[np.ndarray] = None):
         self.save_ply(filepath.replace(".ply", ".pcd"), points, colors)   # dp:442-450 (same quirk)

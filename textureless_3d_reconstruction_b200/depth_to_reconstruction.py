@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .runtime import get_context, write_ply
+from .runtime import get_context, to_host, write_ply
 
 
 @dataclass
@@ -149,7 +149,7 @@ class DenseReconstructor:
         xyz, rgb = self.depth_to_pointcloud_device(
             torch.from_numpy(d).to(dev), torch.from_numpy(np.ascontiguousarray(color, np.uint8)).to(dev),
             pose=pose, scale=scale, subsample=subsample)
-        return xyz.cpu().numpy(), rgb.cpu().numpy()
+        return to_host(xyz), to_host(rgb)
 
     def merge_pointclouds_device(self, points, colors, voxel_size=0.005, remove_outliers=True):
         """points f32|f64 [N,3], colors u8 [N,3] CUDA tensors -> (points f64, colors u8)."""
@@ -176,7 +176,7 @@ class DenseReconstructor:
             p, c = self.merge_pointclouds_device(
                 torch.from_numpy(np.ascontiguousarray(points)).to(dev),
                 torch.from_numpy(np.ascontiguousarray(colors, np.uint8)).to(dev), voxel_size)
-            points, colors = p.cpu().numpy(), c.cpu().numpy()
+            points, colors = to_host(p), to_host(c)
         return points, colors
 
 
@@ -279,7 +279,7 @@ class DepthToReconstructionPipeline:
             return np.array([]), np.array([]), self.camera_poses
         if self.config.voxel_size > 0:
             pts, cols = self.dense.merge_pointclouds_device(pts, cols, self.config.voxel_size)
-        final_points, final_colors = pts.cpu().numpy(), cols.cpu().numpy()
+        final_points, final_colors = to_host(pts), to_host(cols)
         print(f"\nFinal reconstruction: {len(final_points)} points, {len(self.camera_poses)} cameras")
         return final_points, final_colors, self.camera_poses
 
