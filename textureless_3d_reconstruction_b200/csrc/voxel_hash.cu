@@ -138,10 +138,13 @@ __global__ void __launch_bounds__(256)
     double px, py, pz;
     unsigned long long key = 0;
     const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
-    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    // fused clouds are scan-ordered: lanes that share a voxel are almost always neighbours, so only
+    // the first lane of every run of equal keys inserts (a voxel that re-appears later in the warp
+    // is found by the probe, like one that another warp inserted)
+    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     if (!valid) continue;
-    const unsigned peers = __match_any_sync(act, key);
-    if ((int)lane != __ffs(peers) - 1) continue;
+    if (lane != 0 && ((vmask >> (lane - 1)) & 1u) && prev == key) continue;
     unsigned long long slot = mix64(key) & tb.mask;
     bool placed = false;
     for (unsigned long long probe = 0; probe <= tb.mask; ++probe) {
@@ -163,16 +166,15 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
     voxel_accum_kernel(const T* __restrict__ xyz, const uint8_t* __restrict__ rgb, long long n,
                        const __grid_constant__ VoxGrid g, const __grid_constant__ VoxTable tb) {
+  // Segmented reduction over RUNS of equal keys in consecutive lanes (fused clouds are scan-ordered,
+  // so a voxel's points sit next to each other): five shuffle-down steps reduce every run of the
+  // warp at once, whatever the number of distinct voxels; the head lane of a run looks the voxel
+  // id up and issues one red.add per field.  A voxel that shows up in two separate runs simply gets
+  // two updates.  f64 sums of f32 coordinates inside a voxel are exact, so grouping is free.
   const unsigned lane = lane_id();
   for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < n;
        base += (long long)gridDim.x * blockDim.x) {
@@ -182,47 +184,32 @@ __global__ void __launch_bounds__(256)
     const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
     unsigned cr = 0, cg = 0, cb = 0;
     if (valid && rgb) { cr = rgb[i * 3 + 0]; cg = rgb[i * 3 + 1]; cb = rgb[i * 3 + 2]; }
-    const unsigned act = __ballot_sync(0xffffffffu, valid);
-    unsigned peers = 0;
-    unsigned id = 0;
-    if (valid) {
-      peers = __match_any_sync(act, key);
-      if ((int)lane == __ffs(peers) - 1) {  // leader: find the voxel id (pass 1 inserted every key)
-        unsigned long long slot = mix64(key) & tb.mask;
-        while (tb.keys[slot] != key) slot = (slot + 1) & tb.mask;
-        id = tb.ids[slot];
-      }
+    if (!valid) { px = py = pz = 0.0; key = T3D_KEY_EMPTY; }  // its own run, contributes nothing
+    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    // last lane of this lane's run: one below the next head above it
+    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+    const int tail = above ? (int)lane + __ffs(above) - 1 : 31;
+    unsigned cnt = 1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double ox = __shfl_down_sync(0xffffffffu, px, d);
+      const double oy = __shfl_down_sync(0xffffffffu, py, d);
+      const double oz = __shfl_down_sync(0xffffffffu, pz, d);
+      const unsigned orr = __shfl_down_sync(0xffffffffu, cr, d);
+      const unsigned og = __shfl_down_sync(0xffffffffu, cg, d);
+      const unsigned ob = __shfl_down_sync(0xffffffffu, cb, d);
+      const unsigned oc = __shfl_down_sync(0xffffffffu, cnt, d);
+      if ((int)lane + d <= tail) { px += ox; py += oy; pz += oz; cr += orr; cg += og; cb += ob; cnt += oc; }
     }
-    unsigned remaining = act;
-    while (remaining) {  // warp-uniform loop over the distinct voxels of this warp
-      const int L = __ffs(remaining) - 1;
-      const unsigned grp = __shfl_sync(0xffffffffu, peers, L);
-      remaining &= ~grp;
-      if (grp == (1u << L)) {  // singleton group: no reduction needed
-        if ((int)lane == L) {
-          VoxAcc* a = tb.acc + id;
-          atomicAdd(&a->sx, px); atomicAdd(&a->sy, py); atomicAdd(&a->sz, pz);
-          if (rgb) { atomicAdd(&a->r, cr); atomicAdd(&a->g, cg); atomicAdd(&a->b, cb); }
-          atomicAdd(&a->cnt, 1u);
-        }
-        continue;
-      }
-      const bool mem = (grp >> lane) & 1u;
-      const double ax = warp_sum_f64(mem ? px : 0.0);
-      const double ay = warp_sum_f64(mem ? py : 0.0);
-      const double az = warp_sum_f64(mem ? pz : 0.0);
-      unsigned ar = 0, ag = 0, ab = 0;
-      if (rgb) {
-        ar = __reduce_add_sync(0xffffffffu, mem ? cr : 0u);
-        ag = __reduce_add_sync(0xffffffffu, mem ? cg : 0u);
-        ab = __reduce_add_sync(0xffffffffu, mem ? cb : 0u);
-      }
-      if ((int)lane == L) {
-        VoxAcc* a = tb.acc + id;
-        atomicAdd(&a->sx, ax); atomicAdd(&a->sy, ay); atomicAdd(&a->sz, az);
-        if (rgb) { atomicAdd(&a->r, ar); atomicAdd(&a->g, ag); atomicAdd(&a->b, ab); }
-        atomicAdd(&a->cnt, (unsigned)__popc(grp));
-      }
+    if (head && valid) {  // pass 1 inserted every key
+      unsigned long long slot = mix64(key) & tb.mask;
+      while (tb.keys[slot] != key) slot = (slot + 1) & tb.mask;
+      VoxAcc* a = tb.acc + tb.ids[slot];
+      atomicAdd(&a->sx, px); atomicAdd(&a->sy, py); atomicAdd(&a->sz, pz);
+      if (rgb) { atomicAdd(&a->r, cr); atomicAdd(&a->g, cg); atomicAdd(&a->b, cb); }
+      atomicAdd(&a->cnt, cnt);
     }
   }
 }
