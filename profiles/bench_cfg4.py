@@ -70,12 +70,15 @@ def main():
             torch.cuda.synchronize()
             r = ctx.voxel_downsample(p, c, v, sorted_output=False, want_idx=True)        # warm (allocations)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = ctx.voxel_downsample(p, c, v, sorted_output=False, want_idx=True)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
+            ms = float("inf")
+            for _ in range(3):          # best of 3: the first calls still pay torch's cudaMalloc of the output buffers
+                del r
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = ctx.voxel_downsample(p, c, v, sorted_output=False, want_idx=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = min(ms, e0.elapsed_time(e1))
             M = r["m"]
             count_ok = int(r["count"].to(torch.int64).sum().item()) == N
             # idempotence on the voxel centres

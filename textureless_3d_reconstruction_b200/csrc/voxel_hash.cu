@@ -54,13 +54,20 @@ __global__ void bounds_kernel(const T* __restrict__ xyz, long long n, double* pa
   }
 }
 
+// one warp per component (6 warps): lanes stride over the per-CTA partials, shuffle tree at the end
 __global__ void bounds_final_kernel(const double* partial, int nblocks, double* out6) {
-  const int c = threadIdx.x;
+  const int c = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (c >= 6) return;
-  double r = partial[c];
-  for (int b = 1; b < nblocks; ++b)
-    r = c < 3 ? fmin(r, partial[b * 6 + c]) : fmax(r, partial[b * 6 + c]);
-  out6[c] = r;
+  const bool is_min = c < 3;
+  double r = is_min ? 1e300 : -1e300;
+  for (int b = l; b < nblocks; b += 32)
+    r = is_min ? fmin(r, partial[b * 6 + c]) : fmax(r, partial[b * 6 + c]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, r, d);
+    r = is_min ? fmin(r, o) : fmax(r, o);
+  }
+  if (l == 0) out6[c] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -95,6 +102,7 @@ struct VoxTable {
   unsigned long long* keys;   // cap slots, T3D_KEY_EMPTY = free
   unsigned* ids;              // cap slots: dense voxel id of the slot's key
   unsigned long long mask;    // cap - 1
+  unsigned long long max_probe;   // insert gives up (flags[0]) after this many slots
   unsigned long long* key_of_id;  // n entries (M used)
   unsigned long long* counter;    // [0] M
   int* flags;                 // [0] table full, [1] index out of packable range
@@ -131,38 +139,76 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     voxel_keys_kernel(const T* __restrict__ xyz, long long n, const __grid_constant__ VoxGrid g,
                       const __grid_constant__ VoxTable tb) {
+  // A warp takes KR rows of 32 consecutive points per iteration.  Fused clouds are scan-ordered:
+  // lanes that share a voxel are almost always neighbours, so only the first lane of every run of
+  // equal keys inserts (a voxel that re-appears later is found by the probe, like one that another
+  // warp inserted).  The first probe of all KR rows is issued before any of them is resolved: the
+  // kernel is bound by the latency of these random table reads, not by their number.
+  constexpr int KR = 4;
   const unsigned lane = lane_id();
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < n;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long i = base + lane;
-    double px, py, pz;
-    unsigned long long key = 0;
-    const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
-    // fused clouds are scan-ordered: lanes that share a voxel are almost always neighbours, so only
-    // the first lane of every run of equal keys inserts (a voxel that re-appears later in the warp
-    // is found by the probe, like one that another warp inserted)
-    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (!valid) continue;
-    if (lane != 0 && ((vmask >> (lane - 1)) & 1u) && prev == key) continue;
-    unsigned long long slot = mix64(key) & tb.mask;
-    bool placed = false;
-    for (unsigned long long probe = 0; probe <= tb.mask; ++probe) {
-      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + slot));
-      if (k == T3D_KEY_EMPTY) {
-        k = atomicCAS(tb.keys + slot, T3D_KEY_EMPTY, key);
-        if (k == T3D_KEY_EMPTY) {  // this thread created the voxel
-          const unsigned long long id = atomicAdd(tb.counter, 1ull);
-          tb.ids[slot] = (unsigned)id;
-          tb.key_of_id[id] = key;
-          placed = true;
-          break;
-        }
-      }
-      if (k == key) { placed = true; break; }
-      slot = (slot + 1) & tb.mask;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp * (32 * KR); base < n; base += nwarps * (32 * KR)) {
+    unsigned long long key[KR], slot[KR], first[KR];
+    bool ins[KR];
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+      const long long i = base + r * 32 + lane;
+      double px, py, pz;
+      key[r] = 0;
+      const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key[r]);
+      const unsigned long long prev = __shfl_up_sync(0xffffffffu, key[r], 1);
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      ins[r] = valid && !(lane != 0 && ((vmask >> (lane - 1)) & 1u) && prev == key[r]);
+      slot[r] = mix64(key[r]) & tb.mask;
+      first[r] = T3D_KEY_EMPTY;
     }
-    if (!placed) tb.flags[0] = 1;
+#pragma unroll
+    for (int r = 0; r < KR; ++r)
+      if (ins[r]) first[r] = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + slot[r]));
+    unsigned created = 0;  // bit r: this lane's CAS created the voxel of row r (at slot[r])
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+      if (!ins[r]) continue;
+      unsigned long long s = slot[r], k = first[r];
+      bool placed = false;
+      for (unsigned long long probe = 0; probe < tb.max_probe; ++probe) {
+        if (k == T3D_KEY_EMPTY) {
+          k = atomicCAS(tb.keys + s, T3D_KEY_EMPTY, key[r]);
+          if (k == T3D_KEY_EMPTY) {  // this thread created the voxel
+            created |= 1u << r;
+            slot[r] = s;
+            placed = true;
+            break;
+          }
+        }
+        if (k == key[r]) { placed = true; break; }
+        s = (s + 1) & tb.mask;
+        k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + s));
+      }
+      if (!placed) tb.flags[0] = 1;
+    }
+    // dense voxel ids: ONE atomicAdd per warp iteration (a million returning atomics on a single
+    // counter would serialise in L2 and cost more than the whole table traffic)
+    const unsigned mine = __popc(created);
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (unsigned)d) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;  // warp-uniform
+    unsigned long long id0 = 0;
+    if (lane == 31) id0 = atomicAdd(tb.counter, (unsigned long long)total);
+    id0 = __shfl_sync(0xffffffffu, id0, 31) + (incl - mine);
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+      if (!(created & (1u << r))) continue;
+      tb.ids[slot[r]] = (unsigned)id0;
+      tb.key_of_id[id0] = key[r];
+      ++id0;
+    }
   }
 }
 
@@ -248,7 +294,7 @@ __global__ void __launch_bounds__(256)
     if (!rec_key(recs[i], g, tb, key)) continue;
     unsigned long long slot = mix64(key) & tb.mask;
     bool placed = false;
-    for (unsigned long long probe = 0; probe <= tb.mask; ++probe) {
+    for (unsigned long long probe = 0; probe < tb.max_probe; ++probe) {
       unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(tb.keys + slot));
       if (k == T3D_KEY_EMPTY) {
         k = atomicCAS(tb.keys + slot, T3D_KEY_EMPTY, key);
@@ -583,7 +629,7 @@ extern "C" int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t
   T3D_REQUIRE(ctx && min_h && max_h, "t3d_bounds: null argument");
   T3D_REQUIRE(n > 0 && xyz, "t3d_bounds: empty cloud");
   cudaStream_t st = as_stream(stream);
-  const int grid = ctx->num_sms * 4;
+  const int grid = ctx->num_sms * 16;
   int rc = ctx->scratch[6].reserve(sizeof(double) * 6 * (grid + 1));
   if (rc != T3D_OK) return rc;
   double* partial = ctx->scratch[6].as<double>();
@@ -592,7 +638,7 @@ extern "C" int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t
   else
     bounds_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), n, partial);
   T3D_LAUNCH_CHECK();
-  bounds_final_kernel<<<1, 32, 0, st>>>(partial, grid, partial + 6 * grid);
+  bounds_final_kernel<<<1, 192, 0, st>>>(partial, grid, partial + 6 * grid);
   T3D_LAUNCH_CHECK();
   ctx->launches += 2;
   double* h = reinterpret_cast<double*>(ctx->pinned);
@@ -660,50 +706,64 @@ static int voxel_run(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, const uint8_
   g.lim_x = (double)(1ull << bits[0]); g.lim_y = (double)(1ull << bits[1]); g.lim_z = (double)(1ull << bits[2]);
   const int key_bits = bits[0] + bits[1] + bits[2];
 
-  // key table: load factor <= 0.5 w.r.t. the worst case (every point its own voxel)
-  unsigned long long cap = 1024;
-  while (cap < 2ull * (unsigned long long)n) cap <<= 1;
-  if (cap * 12 > ctx->scratch[0].cap && cap * 12 > (8ull << 30)) {  // only probe the driver for big tables
+  // key table.  Worst case (every point its own voxel) needs >= 2 n slots for a load factor <= 0.5,
+  // but depth-map clouds put ~10 points into a voxel: the first attempt uses n / 2 slots — 4x less
+  // memory to clear and, for clouds of tens of millions of points, a table that stays in the
+  // 126 MB L2 instead of costing one DRAM access per probe.  If that table fills beyond 0.7 or an
+  // insert gives up after 64 slots, pass 1 is simply repeated with the worst-case table.
+  unsigned long long cap_full = 1024;
+  while (cap_full < 2ull * (unsigned long long)n) cap_full <<= 1;
+  if (cap_full * 12 > ctx->scratch[0].cap && cap_full * 12 > (8ull << 30)) {  // only probe the driver for big tables
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    while (cap > 1024 && cap * 12 > free_b / 2 + ctx->scratch[0].cap && cap / 2 > (unsigned long long)n + n / 4)
-      cap >>= 1;  // degrade to load factor <= 0.8 before failing
+    while (cap_full > 1024 && cap_full * 12 > free_b / 2 + ctx->scratch[0].cap &&
+           cap_full / 2 > (unsigned long long)n + n / 4)
+      cap_full >>= 1;  // degrade to load factor <= 0.8 before failing
   }
-  if ((rc = ctx->scratch[0].reserve(cap * 12)) != T3D_OK) return rc;
+  unsigned long long cap_try = 1024;
+  while (cap_try < (unsigned long long)n / 2) cap_try <<= 1;
+  if (recs || cap_try > cap_full) cap_try = cap_full;  // partial records: one per voxel and rank already
   if ((rc = ctx->scratch[1].reserve(64)) != T3D_OK) return rc;
   if ((rc = ctx->scratch[2].reserve((size_t)n * 8)) != T3D_OK) return rc;
   VoxTable tb;
   memset(&tb, 0, sizeof(tb));
-  tb.keys = ctx->scratch[0].as<unsigned long long>();
-  tb.ids = reinterpret_cast<unsigned*>(tb.keys + cap);
-  tb.mask = cap - 1;
-  tb.key_of_id = ctx->scratch[2].as<unsigned long long>();
-  tb.flags = ctx->scratch[1].as<int>();
-  tb.counter = reinterpret_cast<unsigned long long*>(tb.flags + 4);
-  tb.sh_y = bits[2];
-  tb.sh_x = bits[1] + bits[2];
-  tr.mark("reserve");
-  T3D_CUDA(cudaMemsetAsync(tb.keys, 0xFF, cap * 8, st));
-  T3D_CUDA(cudaMemsetAsync(tb.flags, 0, 64, st));
-
   const long long warps = (n + 31) / 32;
   const long long want = (warps + 7) / 8;  // 256-thread CTAs
   const int grid = (int)(want < (long long)ctx->num_sms * 16 ? want : (long long)ctx->num_sms * 16);
-  if (recs)
-    rec_keys_kernel<<<grid, 256, 0, st>>>(recs, n, g, tb);
-  else if (xyz_is_f64)
-    voxel_keys_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), n, g, tb);
-  else
-    voxel_keys_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), n, g, tb);
-  T3D_LAUNCH_CHECK();
-  ctx->launches++;
   int* h = reinterpret_cast<int*>(ctx->pinned);
-  T3D_CUDA(cudaMemcpyAsync(h, tb.flags, 64, cudaMemcpyDeviceToHost, st));
-  T3D_CUDA(cudaStreamSynchronize(st));
-  tr.mark("pass1+sync");
-  if (h[0]) { t3d_set_error("t3d_voxel_downsample: hash table full"); return T3D_E_CAPACITY; }
-  if (h[1]) { t3d_set_error("t3d_voxel_downsample: voxel index out of range"); return T3D_E_NUMERIC; }
-  const long long m = (long long)*reinterpret_cast<unsigned long long*>(h + 4);
+  long long m = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const unsigned long long cap = attempt == 0 ? cap_try : cap_full;
+    if ((rc = ctx->scratch[0].reserve(cap * 12)) != T3D_OK) return rc;
+    tb.keys = ctx->scratch[0].as<unsigned long long>();
+    tb.ids = reinterpret_cast<unsigned*>(tb.keys + cap);
+    tb.mask = cap - 1;
+    tb.max_probe = cap < cap_full ? 64 : cap;
+    tb.key_of_id = ctx->scratch[2].as<unsigned long long>();
+    tb.flags = ctx->scratch[1].as<int>();
+    tb.counter = reinterpret_cast<unsigned long long*>(tb.flags + 4);
+    tb.sh_y = bits[2];
+    tb.sh_x = bits[1] + bits[2];
+    tr.mark("reserve");
+    T3D_CUDA(cudaMemsetAsync(tb.keys, 0xFF, cap * 8, st));
+    T3D_CUDA(cudaMemsetAsync(tb.flags, 0, 64, st));
+    if (recs)
+      rec_keys_kernel<<<grid, 256, 0, st>>>(recs, n, g, tb);
+    else if (xyz_is_f64)
+      voxel_keys_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(xyz), n, g, tb);
+    else
+      voxel_keys_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(xyz), n, g, tb);
+    T3D_LAUNCH_CHECK();
+    ctx->launches++;
+    T3D_CUDA(cudaMemcpyAsync(h, tb.flags, 64, cudaMemcpyDeviceToHost, st));
+    T3D_CUDA(cudaStreamSynchronize(st));
+    tr.mark("pass1+sync");
+    if (h[1]) { t3d_set_error("t3d_voxel_downsample: voxel index out of range"); return T3D_E_NUMERIC; }
+    m = (long long)*reinterpret_cast<unsigned long long*>(h + 4);
+    if (cap < cap_full && (h[0] || (double)m > 0.7 * (double)cap)) continue;  // too optimistic: worst-case table
+    if (h[0]) { t3d_set_error("t3d_voxel_downsample: hash table full"); return T3D_E_CAPACITY; }
+    break;
+  }
   if (m > capacity) {
     t3d_set_error("t3d_voxel_downsample: capacity %lld < voxels %lld", (long long)capacity, m);
     return T3D_E_CAPACITY;
