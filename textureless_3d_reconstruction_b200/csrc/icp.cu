@@ -203,11 +203,26 @@ __global__ void hg_count_kernel(const float* __restrict__ tgt, const __grid_cons
 // cells get their [start, start+count) range from a running cursor: cell order is
 // irrelevant, only contiguity inside a cell matters
 __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
+  // the loop bound is warp-uniform (the table size is a multiple of 32 and so is the stride), so the
+  // cursor can be advanced once per warp: tens of thousands of returning atomics on one address
+  // would otherwise serialise in L2
+  const unsigned lane = lane_id();
   for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s <= g.mask;
        s += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned c = g.count[s];
+    unsigned incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (unsigned)d) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(g.cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
     if (!c) continue;
-    g.start[s] = atomicAdd(g.cursor, c);
+    g.start[s] = base + (incl - c);
     // note this fine cell's coarse cell (2h); hg_dilate_kernel then marks the 27 coarse cells around
     // every occupied coarse cell — one dilation per coarse cell instead of one per fine cell
     int fx, fy, fz;
