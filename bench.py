@@ -4,7 +4,7 @@
 Workload (N=1): BASELINE.json configs[1] — TSDF integration of 300 synthetic
 1080x1920 frames (tunnel T1, known poses, 1 cm voxels, 8^3 blocks, trunc 4 cm,
 depth_max 5 m) on one B200.  One "step" = reset the volume and fuse all 300
-frames (K4 touch/allocate + K5 integrate, 32-frame temporally blocked passes).
+frames (K4 touch/allocate + K5 integrate, 64-frame temporally blocked passes).
 N>1: every rank fuses its own 300-frame stretch of the tunnel (frame-stream
 sharding, weak scaling), then blocks outside a rank's z-slab are routed to their
 owner over NCCL and merged.
@@ -310,7 +310,7 @@ def run_ours(args):
         "avg_launch_ms": k5_ms_per_launch, "launches_timed": prof["calls"],
         "temporal_blocking": {
             "frames_per_launch": B,
-            "note": "one launch applies up to 32 frames to a block held in registers, so the block state "
+            "note": "one launch applies up to 64 frames to a block held in registers, so the block state "
                     "(40 B/voxel) crosses HBM once per launch instead of once per frame; `achieved` uses the "
                     "per-frame SURVEY 8d byte count and can therefore exceed the copy peak",
             "batched_min_bytes_per_launch": min_bytes_step / calls_per_step,
@@ -566,7 +566,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=300)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--block-capacity", type=int, default=600_000)
     ap.add_argument("--cpu-frames", type=int, default=300,
                     help="frames of the workload the CPU legs fuse per pass (300 = the whole cfg2 job, ~4 s on 16 cores)")

@@ -217,7 +217,7 @@ void t3d_tsdf_destroy(t3d_tsdf* v);
 /* Forget all blocks (O(hash) memset; block storage is lazily re-initialised). */
 int t3d_tsdf_reset(t3d_tsdf* v, t3d_stream stream);
 
-/* Fuse `n_frames` (1..32) frames in one pass: K4 touch/allocate over all of
+/* Fuse `n_frames` (1..64) frames in one pass: K4 touch/allocate over all of
  * them, then K5 integrates every touched block, each voxel applying its
  * frames in index order (identical arithmetic to n_frames sequential calls).
  * frames_h: host array.  depth_is_u16: depth = raw/depth_scale.  Asynchronous. */
@@ -226,7 +226,7 @@ int t3d_tsdf_integrate(t3d_tsdf* v, const t3d_frame_view* frames_h,
                        float depth_scale, float depth_max, t3d_stream stream);
 
 /* Fuse a whole sequence with known poses (config 2): batches of `batch`
- * (1..32) frames; K4 of batch b+1 runs on an internal stream underneath K5 of
+ * (1..64) frames; K4 of batch b+1 runs on an internal stream underneath K5 of
  * batch b.  Bit-identical to calling t3d_tsdf_integrate batch by batch.
  * Work is ordered after prior work on `stream`, and `stream` ends ordered
  * after all of it.  Asynchronous. */

@@ -76,7 +76,7 @@ def traffic(path, kernel="integrate_kernel"):
                       "dram_read_per_launch": sum(p["read"] for p in per) / n,
                       "dram_write_per_launch": sum(p["write"] for p in per) / n,
                       "source": f"ncu --set full --clock-control none, {path.split('/')[-1]}, mean of {len(per)} launches "
-                                "of one 300-frame step (10 batches of <=32 frames)",
+                                "of one 300-frame step (batches of <= 64 frames)",
                       "per_launch": per}, indent=1))
 
 

@@ -491,7 +491,7 @@ class Context:
 class TSDFVolume:
     """Voxel-block TSDF volume (K4/K5/K6) on one GPU."""
 
-    MAX_BATCH = 32
+    MAX_BATCH = 64
 
     def __init__(self, voxel_size=0.01, sdf_trunc=0.04, block_capacity=200_000, pixel_round=0,
                  ctx: Context | None = None):
@@ -534,12 +534,12 @@ class TSDFVolume:
         return arr
 
     def integrate_views(self, views, start, count, H, W, depth_is_u16=False, depth_scale=1.0, depth_max=5.0):
-        """Fuse views[start:start+count] (count <= 32) in one temporally blocked pass."""
+        """Fuse views[start:start+count] (count <= 64) in one temporally blocked pass."""
         sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
         check(self.lib.t3d_tsdf_integrate(self.handle, sub, int(count), int(H), int(W), int(depth_is_u16),
                                           float(depth_scale), float(depth_max), _stream()))
 
-    def integrate_sequence(self, views, n_frames, H, W, batch=32, depth_is_u16=False, depth_scale=1.0,
+    def integrate_sequence(self, views, n_frames, H, W, batch=64, depth_is_u16=False, depth_scale=1.0,
                            depth_max=5.0, start=0):
         """Fuse views[start:start+n_frames] in `batch`-frame passes with K4/K5 overlap."""
         sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
