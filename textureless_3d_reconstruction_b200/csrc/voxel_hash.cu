@@ -221,41 +221,60 @@ __global__ void __launch_bounds__(256)
   // warp at once, whatever the number of distinct voxels; the head lane of a run looks the voxel
   // id up and issues one red.add per field.  A voxel that shows up in two separate runs simply gets
   // two updates.  f64 sums of f32 coordinates inside a voxel are exact, so grouping is free.
+  constexpr int AR = 2;  // rows of 32 points per warp iteration: two table look-ups in flight per head lane
   const unsigned lane = lane_id();
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < n;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long i = base + lane;
-    double px = 0.0, py = 0.0, pz = 0.0;
-    unsigned long long key = 0;
-    const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px, py, pz, key);
-    unsigned cr = 0, cg = 0, cb = 0;
-    if (valid && rgb) { cr = rgb[i * 3 + 0]; cg = rgb[i * 3 + 1]; cb = rgb[i * 3 + 2]; }
-    if (!valid) { px = py = pz = 0.0; key = T3D_KEY_EMPTY; }  // its own run, contributes nothing
-    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || prev != key;
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    // last lane of this lane's run: one below the next head above it
-    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-    const int tail = above ? (int)lane + __ffs(above) - 1 : 31;
-    unsigned cnt = 1;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp * (32 * AR); base < n; base += nwarps * (32 * AR)) {
+    double px[AR], py[AR], pz[AR];
+    unsigned cr[AR], cg[AR], cb[AR], cnt[AR];
+    unsigned long long key[AR], slot[AR], first[AR];
+    bool emit[AR];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double ox = __shfl_down_sync(0xffffffffu, px, d);
-      const double oy = __shfl_down_sync(0xffffffffu, py, d);
-      const double oz = __shfl_down_sync(0xffffffffu, pz, d);
-      const unsigned orr = __shfl_down_sync(0xffffffffu, cr, d);
-      const unsigned og = __shfl_down_sync(0xffffffffu, cg, d);
-      const unsigned ob = __shfl_down_sync(0xffffffffu, cb, d);
-      const unsigned oc = __shfl_down_sync(0xffffffffu, cnt, d);
-      if ((int)lane + d <= tail) { px += ox; py += oy; pz += oz; cr += orr; cg += og; cb += ob; cnt += oc; }
+    for (int r = 0; r < AR; ++r) {
+      const long long i = base + r * 32 + lane;
+      px[r] = py[r] = pz[r] = 0.0;
+      key[r] = 0;
+      const bool valid = i < n && voxel_key_of(xyz, i, g, tb, px[r], py[r], pz[r], key[r]);
+      cr[r] = cg[r] = cb[r] = 0;
+      if (valid && rgb) { cr[r] = rgb[i * 3 + 0]; cg[r] = rgb[i * 3 + 1]; cb[r] = rgb[i * 3 + 2]; }
+      if (!valid) { px[r] = py[r] = pz[r] = 0.0; key[r] = T3D_KEY_EMPTY; }  // its own run, contributes nothing
+      const unsigned long long prev = __shfl_up_sync(0xffffffffu, key[r], 1);
+      const bool head = lane == 0 || prev != key[r];
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      // last lane of this lane's run: one below the next head above it
+      const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+      const int tail = above ? (int)lane + __ffs(above) - 1 : 31;
+      cnt[r] = 1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double ox = __shfl_down_sync(0xffffffffu, px[r], d);
+        const double oy = __shfl_down_sync(0xffffffffu, py[r], d);
+        const double oz = __shfl_down_sync(0xffffffffu, pz[r], d);
+        const unsigned orr = __shfl_down_sync(0xffffffffu, cr[r], d);
+        const unsigned og = __shfl_down_sync(0xffffffffu, cg[r], d);
+        const unsigned ob = __shfl_down_sync(0xffffffffu, cb[r], d);
+        const unsigned oc = __shfl_down_sync(0xffffffffu, cnt[r], d);
+        if ((int)lane + d <= tail) {
+          px[r] += ox; py[r] += oy; pz[r] += oz; cr[r] += orr; cg[r] += og; cb[r] += ob; cnt[r] += oc;
+        }
+      }
+      emit[r] = head && valid;
+      slot[r] = mix64(key[r]) & tb.mask;
+      first[r] = 0;
     }
-    if (head && valid) {  // pass 1 inserted every key
-      unsigned long long slot = mix64(key) & tb.mask;
-      while (tb.keys[slot] != key) slot = (slot + 1) & tb.mask;
-      VoxAcc* a = tb.acc + tb.ids[slot];
-      atomicAdd(&a->sx, px); atomicAdd(&a->sy, py); atomicAdd(&a->sz, pz);
-      if (rgb) { atomicAdd(&a->r, cr); atomicAdd(&a->g, cg); atomicAdd(&a->b, cb); }
-      atomicAdd(&a->cnt, cnt);
+#pragma unroll
+    for (int r = 0; r < AR; ++r)
+      if (emit[r]) first[r] = tb.keys[slot[r]];
+#pragma unroll
+    for (int r = 0; r < AR; ++r) {
+      if (!emit[r]) continue;  // pass 1 inserted every key
+      unsigned long long sl = slot[r], k = first[r];
+      while (k != key[r]) { sl = (sl + 1) & tb.mask; k = tb.keys[sl]; }
+      VoxAcc* a = tb.acc + tb.ids[sl];
+      atomicAdd(&a->sx, px[r]); atomicAdd(&a->sy, py[r]); atomicAdd(&a->sz, pz[r]);
+      if (rgb) { atomicAdd(&a->r, cr[r]); atomicAdd(&a->g, cg[r]); atomicAdd(&a->b, cb[r]); }
+      atomicAdd(&a->cnt, cnt[r]);
     }
   }
 }
