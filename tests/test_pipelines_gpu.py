@@ -98,6 +98,14 @@ def test_der_cli_tracks_and_writes_ply(ctx, tmp_path, capsys):
         P[:3, :3], P[:3, 3:4] = cam[i]
         E = P @ np.linalg.inv(rel_gt)
         assert np.linalg.norm(E[:3, 3]) < 0.03, (i, E[:3, 3])
+    # (extension) the fused surface as a triangle mesh, Open3D write_triangle_mesh layout
+    nv, nt = rec.save_mesh(tmp_path / "o" / "reconstruction_mesh.ply")
+    raw = (tmp_path / "o" / "reconstruction_mesh.ply").read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    assert f"element vertex {nv}".encode() in head and f"element face {nt}".encode() in head and nt > 10000
+    assert len(body) == nv * (6 * 8 + 3) + nt * 13
+    faces = np.frombuffer(body[nv * 51:], np.dtype([("k", "u1"), ("i", "<u4", 3)]))
+    assert (faces["k"] == 3).all() and int(faces["i"].max()) < nv
     # CLI: fewer than two images -> exit(1) like the reference (der:1452-1454)
     empty = tmp_path / "empty"
     empty.mkdir()

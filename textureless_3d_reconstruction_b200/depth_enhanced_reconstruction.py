@@ -209,6 +209,19 @@ class DepthEnhancedReconstruction:
         self._save_pointcloud(all_points, all_colors, out / "reconstruction.ply")
         return all_points, all_colors, self.camera_poses
 
+    def save_mesh(self, filepath, weight_threshold: float = 1.0):
+        """(extension) Triangle mesh of the fused volume -> .ply in Open3D's write_triangle_mesh
+        layout (K10 marching cubes; north_star "surface/point extraction to .ply").  Call after
+        reconstruct().  Returns (n_vertices, n_triangles)."""
+        from .runtime import write_ply_mesh
+        v, n, c, t = self.volume.extract_mesh(weight_threshold)
+        if t.shape[0] == 0:
+            print("No surface to save")
+            return 0, 0
+        write_ply_mesh(filepath, v, t, colors=c, normals=n)
+        print(f"Saved mesh with {v.shape[0]} vertices and {t.shape[0]} triangles to {filepath}")
+        return int(v.shape[0]), int(t.shape[0])
+
     def _save_pointcloud(self, points: np.ndarray, colors: np.ndarray, filepath: Path):
         """der:1283-1311."""
         if len(points) == 0:
@@ -230,6 +243,8 @@ def main(argv=None):
     parser.add_argument("--no-depth", action="store_true", help="Disable depth estimation")
     parser.add_argument("--no-hybrid", action="store_true", help="Disable hybrid features")
     parser.add_argument("--depth-folder", type=str, default=None, help="(extension) folder with depth maps")
+    parser.add_argument("--mesh", action="store_true",
+                        help="(extension) also write <output>/reconstruction_mesh.ply (marching-cubes triangle mesh)")
     args = parser.parse_args(argv)
     K = np.array([[args.fx, 0, args.cx], [0, args.fy, args.cy], [0, 0, 1]], dtype=np.float64)
     rec = DepthEnhancedReconstruction(K=K, use_depth=not args.no_depth, use_hybrid_features=not args.no_hybrid)
@@ -239,6 +254,8 @@ def main(argv=None):
     rec.load_depths(args.depth_folder or args.input)
     if rec.reconstruct(output_dir=args.output) is None:
         print("Reconstruction failed")
+    elif args.mesh:
+        rec.save_mesh(Path(args.output) / "reconstruction_mesh.ply")
 
 
 if __name__ == "__main__":
