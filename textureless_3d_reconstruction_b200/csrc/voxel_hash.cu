@@ -71,20 +71,19 @@ __global__ void bounds_final_kernel(const double* partial, int nblocks, double* 
 }
 
 // ---------------------------------------------------------------------------
-// voxel hash — two passes over the points, both warp-aggregated.
+// voxel hash — two passes over the points, both aggregated over RUNS of equal keys in
+// consecutive lanes (fused clouds are scan-ordered: a voxel's points sit next to each other).
 //
-//   pass 1 (voxel_keys_kernel)   key table only: the lanes of a warp that fall
-//       into the same voxel elect one leader (__match_any_sync); only leaders
-//       touch the table.  The CAS winner of a slot takes the next dense voxel id
-//       from a counter and records key_of_id[id].  Depth-map clouds put tens of
-//       neighbouring points into one voxel, so this removes >90 % of the table
-//       traffic and all same-address CAS storms.
+//   pass 1 (voxel_keys_kernel)   key table only: the first lane of every run inserts its key
+//       (a voxel that re-appears later is found by the probe).  A warp takes four rows of 32
+//       points per iteration and issues the first probe of all of them before resolving any;
+//       the CAS winners of a warp iteration take their dense voxel ids from ONE atomicAdd.
+//       The table starts at n/2 slots (retry with the worst-case 2n if it fills beyond 0.7).
 //   (host reads M — the only size the accumulators need)
-//   pass 2 (voxel_accum_kernel)  leaders look their voxel id up, the warp
-//       reduces each group (f64 xor-shuffle tree for xyz, redux.sync for the
-//       integer colour sums and the count) and the leader issues ONE red.add
-//       per accumulator.  Accumulators are M 64-byte records (one per voxel),
-//       not per-slot, so nothing of size O(table) is ever zeroed or scanned.
+//   pass 2 (voxel_accum_kernel)  a 5-step segmented shuffle-down reduces every run of the
+//       warp at once; run heads look the voxel id up and issue ONE red.add per accumulator
+//       field.  Accumulators are M 64-byte records (one per voxel), not per-slot, so nothing
+//       of size O(table) is ever scanned.
 //
 // Memory: 12 B per table slot (>= 2 N slots) + 8 B per point of key scratch + 64 B
 // per output voxel, instead of 48 B per slot.  f64 sums of f32 inputs that lie
