@@ -323,3 +323,18 @@ def test_sharded_statistical_outlier_world2(oracle):
     ref_keep = ref["keep"] if isinstance(ref, dict) else ref[0]
     assert np.array_equal(res[0][1].astype(bool), np.asarray(ref_keep).astype(bool))
     assert not res[0][1][:5].any()
+
+
+def test_overlap_order_puts_the_tail_first_and_the_head_last():
+    """Frame order of routing-underneath-fusion: batches descending, frames ascending inside a batch;
+    the first batch holds every frame that can reach past the slab, the last batch the slab's head."""
+    for n, b in [(300, 64), (300, 32), (64, 64), (100, 24), (7, 3)]:
+        order = D.P2PBlockRouter.overlap_order(n, b)
+        assert sorted(order) == list(range(n))
+        assert order[:min(b, n)] == list(range(max(0, n - b), n))            # tail batch first, in frame order
+        nb = -(-n // b)
+        last = order[(nb - 1) * b:] if nb > 1 else order
+        assert last[0] == 0 and last == list(range(len(last)))                # head batch last
+        for k in range(0, n, b):                                              # ascending inside every batch
+            chunk = order[k:k + b]
+            assert chunk == sorted(chunk)
