@@ -231,3 +231,57 @@ def test_gpu_mesh_empty_and_truncated(ctx, oracle):
                                         _stream()))
     assert cnt.tolist() == [len(full[0]), len(full[3])]
     assert (xyz[vcap:] == -7.0).all() and (tri[tcap:] == -7).all()
+
+
+def test_oracle_vertex_set_vs_numpy_restatement(oracle):
+    """Independent NumPy restatement of which edges carry a vertex (sign-bit change on an edge of at
+    least one cube whose 8 corners all have W >= thr), on a dense grid with a ragged observed region."""
+    lo, hi = 0, 3
+    keys, t, w, rgb = analytic_blocks(gyroid, lo, hi, VOXEL, TRUNC)
+    rng = np.random.default_rng(8)
+    w[rng.uniform(size=w.shape) < 0.08] = 1.0                     # unobserved-enough voxels punch holes
+    ov = oracle.TSDFVolume(VOXEL, TRUNC)
+    ov.import_blocks(keys, t, w, rgb)
+    xyz, _, _, tri = ov.extract_mesh(3.0)
+    n = (hi - lo) * 8
+    T = np.zeros((n, n, n), np.float32)
+    W = np.zeros((n, n, n), np.float32)
+    v = np.arange(512)
+    loc = np.stack([v & 7, (v >> 3) & 7, v >> 6], -1)
+    for k, tt, ww in zip(keys, t, w):
+        g = (k - lo) * 8 + loc
+        T[g[:, 0], g[:, 1], g[:, 2]] = tt
+        W[g[:, 0], g[:, 1], g[:, 2]] = ww
+    ok = W >= 3.0
+    cube = np.ones((n - 1, n - 1, n - 1), bool)                   # cube based at (x,y,z) valid
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                cube &= ok[dx:n - 1 + dx, dy:n - 1 + dy, dz:n - 1 + dz]
+    neg = T < 0
+    expected = 0
+    for ax in range(3):
+        a = [slice(0, n)] * 3
+        b = [slice(0, n)] * 3
+        a[ax], b[ax] = slice(0, n - 1), slice(1, n)
+        change = neg[tuple(a)] != neg[tuple(b)]                   # edge (voxel, +ax), shape n-1 along ax
+        # the edge belongs to the cubes based at voxel - {0,1} along the two other axes
+        o1, o2 = [c for c in range(3) if c != ax]
+        used = np.zeros_like(change)
+        pad = np.zeros((n + 1, n + 1, n + 1), bool)
+        pad[1:n, 1:n, 1:n] = cube                                 # pad[i+1] = cube[i]; index -1 and n-1.. are False
+        for s1 in (0, 1):
+            for s2 in (0, 1):
+                idx = [None, None, None]
+                idx[ax] = slice(1, n)
+                idx[o1] = slice(1 - s1, n + 1 - s1)
+                idx[o2] = slice(1 - s2, n + 1 - s2)
+                used |= pad[tuple(idx)]
+        expected += int((change & used).sum())
+    assert len(xyz) == expected
+    cases = np.zeros((n - 1, n - 1, n - 1), np.int32)
+    corner = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    for i, (dx, dy, dz) in enumerate(corner):
+        cases |= neg[dx:n - 1 + dx, dy:n - 1 + dy, dz:n - 1 + dz].astype(np.int32) << i
+    crossed = cube & (cases != 0) & (cases != 255)
+    assert crossed.sum() > 1000 and len(tri) >= crossed.sum()     # every crossed valid cube emits >= 1 triangle
