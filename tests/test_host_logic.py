@@ -138,3 +138,33 @@ def test_ply_writers_host_only(tmp_path):
         assert line == f"{row[0]} {row[1]} {row[2]} 0 0 0"                       # Python repr rules
     with pytest.raises(_lib.T3DError):
         write_ply(tmp_path / "no_such_dir" / "x.ply", vals, cols)
+
+
+def test_ply_ascii_writer_threaded_path_is_byte_exact(tmp_path):
+    """Above 200 k points the ASCII writer formats chunks on all host threads: the file must still be
+    the reference's line-by-line output (`f"{x} {y} {z} {r} {g} {b}\\n"`, d2r:700-701), in order."""
+    import time
+    from textureless_3d_reconstruction_b200 import _lib
+    from textureless_3d_reconstruction_b200.runtime import write_ply
+    rng = np.random.default_rng(12)
+    n = 450_001
+    pts = (rng.normal(size=(n, 3)) * np.array([3.0, 1e-3, 250.0])).astype(np.float32)
+    pts[::1000] = 0.0
+    cols = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    f = tmp_path / "big.ply"
+    t0 = time.perf_counter()
+    write_ply(f, pts, cols, layout=_lib.PLY_REF_ASCII)
+    dt = time.perf_counter() - t0
+    head, body = f.read_text().split("end_header\n")
+    assert f"element vertex {n}" in head
+    lines = body.split("\n")
+    assert lines[-1] == "" and len(lines) == n + 1
+    p64 = pts.astype(np.float64)
+    for i in list(range(0, n, 997)) + [n - 1, 224_999, 225_000, 225_001]:
+        x, y, z = (float(v) for v in p64[i])
+        assert lines[i] == f"{x} {y} {z} {cols[i, 0]} {cols[i, 1]} {cols[i, 2]}", i
+    # single-chunk reference: the same points written in two halves through the small-n path
+    g = tmp_path / "half.ply"
+    write_ply(g, pts[:150_000], cols[:150_000], layout=_lib.PLY_REF_ASCII)
+    assert g.read_text().split("end_header\n")[1] == "\n".join(lines[:150_000]) + "\n"
+    assert dt < 30

@@ -11,6 +11,8 @@
 //                       `property float`, one "x y z r g b" line per point where
 //                       x,y,z are Python's repr of the value promoted to double.
 #include <charconv>
+#include <functional>
+#include <thread>
 
 #include "common.cuh"
 
@@ -105,22 +107,45 @@ extern "C" int t3d_write_ply_h(const char* path, const void* xyz_h, int xyz_is_f
                  "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\n"
                  "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"
                  "end_header\n", (long long)n) > 0;
-    char line[160];
-    for (int64_t i = 0; i < n; ++i) {
-      int o = 0;
-      for (int c = 0; c < 3; ++c) {
-        const double v = xyz_is_f64 ? xd[i * 3 + c] : (double)xf[i * 3 + c];
-        o += py_repr(v, line + o);
-        line[o++] = ' ';
+    // shortest-repr formatting is the whole cost (~0.2 us per number): super-chunks of 2 M points are
+    // formatted by all host threads into per-thread buffers and written in order
+    auto format_range = [&](int64_t a, int64_t b, std::vector<char>& out) {
+      out.clear();
+      out.reserve((size_t)(b - a) * 64);
+      char line[160];
+      for (int64_t i = a; i < b; ++i) {
+        int o = 0;
+        for (int c = 0; c < 3; ++c) {
+          const double v = xyz_is_f64 ? xd[i * 3 + c] : (double)xf[i * 3 + c];
+          o += py_repr(v, line + o);
+          line[o++] = ' ';
+        }
+        for (int c = 0; c < 3; ++c) {
+          o += put_uint(rgb_h ? rgb_h[i * 3 + c] : 0u, line + o);
+          line[o++] = c == 2 ? '\n' : ' ';
+        }
+        out.insert(out.end(), line, line + o);
       }
-      for (int c = 0; c < 3; ++c) {
-        o += put_uint(rgb_h ? rgb_h[i * 3 + c] : 0u, line + o);
-        line[o++] = c == 2 ? '\n' : ' ';
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 1 : (nt > 32 ? 32 : nt);
+    if (n < 200000) nt = 1;
+    const int64_t super = 2000000;
+    std::vector<std::vector<char>> parts(nt);
+    for (int64_t s0 = 0; s0 < n && ok; s0 += super) {
+      const int64_t s1 = s0 + super < n ? s0 + super : n;
+      const int64_t per = (s1 - s0 + nt - 1) / nt;
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nt; ++t) {
+        const int64_t a = s0 + (int64_t)t * per, b = a + per < s1 ? a + per : s1;
+        if (a < b) th.emplace_back(format_range, a, b, std::ref(parts[t]));
+        else parts[t].clear();
       }
-      buf.insert(buf.end(), line, line + o);
-      if (buf.size() > (1 << 22) - 256) flush();
+      format_range(s0, s0 + per < s1 ? s0 + per : s1, parts[0]);
+      for (auto& t : th) t.join();
+      for (unsigned t = 0; t < nt && ok; ++t)
+        if (!parts[t].empty()) ok = fwrite(parts[t].data(), 1, parts[t].size(), f) == parts[t].size();
     }
-    flush();
   } else {
     ok = ok && fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\n"
                           "element vertex %lld\nproperty double x\nproperty double y\n"
