@@ -39,6 +39,7 @@ def lib():
         _lib.o_tsdf_create.restype = C.c_void_p
         _lib.o_tsdf_touch.restype = C.c_int64
         _lib.o_tsdf_num_blocks.restype = C.c_int64
+        _lib.o_tsdf_export_flags.restype = C.c_int64
         _lib.o_tsdf_extract.restype = C.c_int64
         _lib.o_tsdf_extract_view.restype = C.c_int64
         _lib.o_icp_point_to_plane.restype = C.c_int
@@ -183,7 +184,9 @@ class TSDFVolume:
                                C.c_float(depth_scale), C.c_float(depth_max), _p(out))
         return out[:n].copy()
 
-    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0, keys=None):
+    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0, keys=None, literal=False):
+        """R4 + R5 for one frame.  literal=True: R5 exactly as SURVEY 8c writes it (true divisions, no FMA,
+        no reciprocals; o_tsdf_integrate_literal) instead of the kernel-ordered arithmetic."""
         depth, u16 = self._depth(depth)
         H, W = depth.shape
         bgr = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
@@ -192,9 +195,18 @@ class TSDFVolume:
         if keys is None:
             keys = self.touch(depth, K, T, depth_scale, depth_max)
         keys = np.ascontiguousarray(keys, np.int32)
-        lib().o_tsdf_integrate(self._h, _p(depth), C.c_int(u16), _p(bgr), C.c_int(H), C.c_int(W), _p(K), _p(T),
-                               C.c_float(depth_scale), C.c_float(depth_max), _p(keys), C.c_int64(len(keys)))
+        fn = lib().o_tsdf_integrate_literal if literal else lib().o_tsdf_integrate
+        fn(self._h, _p(depth), C.c_int(u16), _p(bgr), C.c_int(H), C.c_int(W), _p(K), _p(T),
+           C.c_float(depth_scale), C.c_float(depth_max), _p(keys), C.c_int64(len(keys)))
         return keys
+
+    def export_flags(self):
+        """(flags u8 [nb, 512] in export() block order, n_sensitive voxel-frame pairs) of a volume fused
+        with literal=True: bit 0 = the literal and the kernel-ordered R5 picked different pixels for some
+        frame, bit 1 = same pixel but a different outcome of the zc / sdf tests."""
+        flags = np.zeros((self.num_blocks, 512), np.uint8)
+        n = lib().o_tsdf_export_flags(self._h, _p(flags))
+        return flags, int(n)
 
     @property
     def num_blocks(self):

@@ -162,3 +162,151 @@ def test_r5_vs_numpy_projective_tsdf(oracle):
         if m.any():
             assert np.abs(ot[b][vi][m] - ts[m]).max() < 1e-4
     assert bad == 0 and checked > 2000
+
+
+def test_r4_vs_numpy_block_keys(oracle):
+    """R4 (block allocation): a vectorised NumPy restatement over the whole stride-4 grid.
+    (i) the same f32 operation sequence => the key SET must be identical;
+    (ii) evaluated in float64 => every key of a sample that is not within 1e-4 block of a block face
+         must be in the oracle's set, and every oracle key must come from some sample's f64 key or from a
+         face-boundary sample (no key the geometry does not imply)."""
+    H, W = 120, 68
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    f32 = np.float32
+    for frame, voxel, trunc, dmax in ((0, 0.01, 0.04, 5.0), (7, 0.02, 0.08, 3.5), (3, 0.005, 0.02, 5.0)):
+        d, c, T = S.synth_frame(0, frame, H, W, *K, noise_sigma=0.002)
+        vol = oracle.TSDFVolume(voxel, trunc)
+        okeys = vol.touch(d, K, T, 1.0, dmax)
+        oset = set(map(tuple, okeys.tolist()))
+        assert len(oset) == len(okeys) > 20                              # unique, first-touch order
+        T32 = np.asarray(T, f32)[:3, :4]
+        R, t = T32[:, :3], T32[:, 3]
+        Rwc = R.T.copy()
+        o = (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(f32)
+        fx, fy, cx, cy = (f32(x) for x in K)
+        bs = f32(voxel) * f32(8.0)
+        tr, dm = f32(trunc), f32(dmax)
+        py, px = np.meshgrid(np.arange(H // 4) * 4, np.arange(W // 4) * 4, indexing="ij")
+        dd = d[py, px].astype(f32) / f32(1.0)
+        valid = (dd > 0) & (dd < dm)
+        xc = (px.astype(f32) - cx) / fx
+        yc = (py.astype(f32) - cy) / fy
+        g = [((Rwc[i, 0] * xc + Rwc[i, 1] * yc) + Rwc[i, 2] * f32(1.0)) + o[i] for i in range(3)]
+        dirv = [g[i] - o[i] for i in range(3)]
+        t_min = np.maximum(dd - tr, f32(0.0))
+        t_max = np.minimum(dd + tr, dm)
+        step = (t_max - t_min) / f32(3.0)
+        assert all(a.dtype == f32 for a in (xc, yc, g[0], dirv[0], step))
+        tt = t_min.copy()
+        got32, must64, may64 = set(), set(), set()
+        for s in range(4):
+            k32 = [np.floor((o[i] + tt * dirv[i]) / bs).astype(np.int64) for i in range(3)]
+            got32 |= set(zip(*(k[valid].tolist() for k in k32)))
+            # float64 evaluation of the same geometry
+            q = [(np.float64(o[i]) + tt.astype(np.float64) * dirv[i].astype(np.float64)) / np.float64(bs) for i in range(3)]
+            near = np.zeros_like(valid)
+            for qi in q:
+                near |= np.abs(qi - np.round(qi)) < 1e-4
+            k64 = [np.floor(qi).astype(np.int64) for qi in q]
+            must64 |= set(zip(*(k[valid & ~near].tolist() for k in k64)))
+            may64 |= set(zip(*(k[valid].tolist() for k in k64)))
+            for sh in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):   # face-boundary samples
+                may64 |= set(zip(*((k64[i][valid & near] + sh[i]).tolist() for i in range(3))))
+            tt = tt + step
+        assert got32 == oset                                              # (i) bit-exact key set
+        assert must64 <= oset <= may64                                    # (ii) geometry, independent of f32 order
+        assert len(must64) > 0.95 * len(oset)
+
+
+def test_r6_vs_numpy_dense_grid(oracle):
+    """R6 (surface points): rebuild a dense (tsdf, weight) grid from the exported blocks and restate the
+    extraction with shifted-array NumPy operations; positions, normals and colours must be the same
+    multiset, bit for bit (same f32 formulas, independent traversal / neighbour lookup)."""
+    H, W = 120, 68
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    f32 = np.float32
+    voxel = 0.02
+    vol = oracle.TSDFVolume(voxel, 0.08)
+    for i in range(5):
+        d, c, T = S.synth_frame(0, i, H, W, *K, noise_sigma=0.002)
+        vol.integrate(d, c, K, T, 1.0, 5.0)
+    thr = 2.0
+    keys, tsdf, w, rgb = vol.export()
+    lo = keys.min(0) - 1                                   # one empty block of margin on every side
+    dims = (keys.max(0) - lo + 2) * 8
+    Tg = np.zeros(dims, f32)                               # missing block: tsdf reads as 0 (gradients) ...
+    Wg = np.full(dims, -1.0, f32)                          # ... and weight as "absent"
+    Cg = np.zeros(tuple(dims) + (3,), f32)
+    for b, k in enumerate(keys):
+        x0, y0, z0 = (k - lo) * 8
+        # block layout: voxel index = x + 8 y + 64 z
+        Tg[x0:x0 + 8, y0:y0 + 8, z0:z0 + 8] = tsdf[b].reshape(8, 8, 8).transpose(2, 1, 0)
+        Wg[x0:x0 + 8, y0:y0 + 8, z0:z0 + 8] = w[b].reshape(8, 8, 8).transpose(2, 1, 0)
+        Cg[x0:x0 + 8, y0:y0 + 8, z0:z0 + 8] = rgb[b].reshape(8, 8, 8, 3).transpose(2, 1, 0, 3)
+    core = tuple(slice(8, n - 8) for n in dims)            # voxels that can own a point
+
+    def sh(a, dx, dy, dz):                                 # a[x+dx, y+dy, z+dz] on the core region
+        return a[8 + dx:dims[0] - 8 + dx, 8 + dy:dims[1] - 8 + dy, 8 + dz:dims[2] - 8 + dz]
+
+    gx, gy, gz = np.meshgrid(*(np.arange(8, n - 8) + l * 8 for n, l in zip(dims, lo)), indexing="ij")
+    rows = []
+    for ax in range(3):
+        e = [int(ax == 0), int(ax == 1), int(ax == 2)]
+        t_o, w_o, t_i, w_i = Tg[core], Wg[core], sh(Tg, *e), sh(Wg, *e)
+        m = (w_o >= thr) & (w_i >= thr) & (t_o * t_i < 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = (f32(0) - t_o) / (t_i - t_o)
+        r = ratio[m]
+        P = [f32(voxel) * ((g[m].astype(f32) + r) if e[i] else g[m].astype(f32)) for i, g in enumerate((gx, gy, gz))]
+        om = f32(1) - r
+        N = []
+        for c_ in range(3):
+            ce = [int(c_ == 0), int(c_ == 1), int(c_ == 2)]
+            go = sh(Tg, *ce)[m] - sh(Tg, *[-x for x in ce])[m]
+            gi = sh(Tg, *[a + b for a, b in zip(e, ce)])[m] - sh(Tg, *[a - b for a, b in zip(e, ce)])[m]
+            N.append(om * go + r * gi)
+        ln = np.sqrt((N[0] * N[0] + N[1] * N[1]) + N[2] * N[2])
+        N = [np.where(ln > 0, n / np.where(ln > 0, ln, 1), n).astype(f32) for n in N]
+        co, ci = Cg[core][m], sh(Cg, *e)[m]
+        col = np.clip(om[:, None] * co + r[:, None] * ci, 0, 255)
+        col = np.floor(col + f32(0.5)).astype(np.uint32)                # roundf for non-negative values
+        rows.append(np.column_stack([np.column_stack(P).view(np.uint32), np.column_stack(N).view(np.uint32), col]))
+    mine = np.concatenate(rows)
+    op, on, oc = vol.extract_points(thr)
+    theirs = np.column_stack([op.view(np.uint32), on.view(np.uint32), oc.astype(np.uint32)])
+    assert len(mine) == len(theirs) > 500
+    mine = mine[np.lexsort(mine.T[::-1])]
+    theirs = theirs[np.lexsort(theirs.T[::-1])]
+    assert np.array_equal(mine[:, :3], theirs[:, :3])                   # positions: bit-exact
+    assert np.array_equal(mine[:, 3:6], theirs[:, 3:6])                 # normals: bit-exact
+    assert np.array_equal(mine[:, 6:], theirs[:, 6:])                   # colours
+
+
+@pytest.mark.parametrize("pixel_round", [0, 1])
+def test_r5_literal_vs_kernel_ordered_formulation(oracle, pixel_round):
+    """o_tsdf_integrate (the arithmetic order the CUDA kernel uses) against o_tsdf_integrate_literal (SURVEY 8c
+    R5 term by term: true divisions, roundf, no FMA, no reciprocals): identical weights except on the voxels the
+    literal oracle marks as formulation-sensitive (pixel-rounding / image-border / threshold boundaries), tsdf
+    within north_star's 1e-4 elsewhere.  The full-size version (1080x1920, 2160x3840) runs on the GPU box
+    (tests/test_tsdf_fullsize_gpu.py) with the CUDA kernel as the third party."""
+    H, W = 240, 136
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    a, b = oracle.TSDFVolume(0.01, 0.04, pixel_round), oracle.TSDFVolume(0.01, 0.04, pixel_round)
+    for i in range(6):
+        d, c, T = S.synth_frame(0, i, H, W, *K, noise_sigma=0.002)
+        keys = a.integrate(d, c, K, T, 1.0, 5.0)
+        b.integrate(d, c, K, T, 1.0, 5.0, keys=keys, literal=True)
+    ka, ta, wa, ca = a.export()
+    kb, tb, wb, cb = b.export()
+    flags, n_pairs = b.export_flags()
+    assert np.array_equal(ka, kb)
+    sens = flags != 0
+    upd = a.counters()["voxel_updates"]
+    assert upd > 500_000 and 0 < n_pairs < 2e-3 * upd
+    assert not ((wa != wb) & ~sens).any()
+    assert np.abs(ta - tb)[~sens].max() <= 1e-4
+    assert np.abs(ca - cb)[~sens].max() <= 1e-2
+    assert abs(a.counters()["voxel_updates"] - b.counters()["voxel_updates"]) <= n_pairs
