@@ -240,12 +240,14 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
  * into the last batch):
  *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch 0 — every
  *     block batch 0 touches exists and no allocation is in flight at that point;
- *   after_batch0(user, event): called ON THE HOST, inside this call, right after K5 of batch 0
- *     was enqueued; `event` (a cudaEvent_t) completes with it.  The callee enqueues its own
- *     work on another stream (t3d_stream_wait_event) and records its completion event;
+ *   after_batch0(user, touch_event, event): called ON THE HOST, inside this call, right after K5 of
+ *     batch 0 was enqueued; `touch_event` (a cudaEvent_t) completes with K4 of batch 0 (from then on
+ *     nblocks_after_touch0 and the keys of those blocks are final), `event` with K5 of batch 0.  The
+ *     callee enqueues its own work on another stream (t3d_stream_wait_event) and records its
+ *     completion event;
  *   wait_before_last (cudaEvent_t, nullable): K4 and K5 of the last batch wait for it.
  * Needs at least 2 batches when any hook is given. */
-typedef void (*t3d_sequence_hook)(void* user, void* event_after_batch0);
+typedef void (*t3d_sequence_hook)(void* user, void* event_after_touch0, void* event_after_batch0);
 int t3d_tsdf_integrate_sequence_hooked(t3d_tsdf* v, const t3d_frame_view* frames_h,
                                        int n_frames, int batch, int H, int W,
                                        int depth_is_u16, float depth_scale, float depth_max,
@@ -324,6 +326,25 @@ int t3d_tsdf_route_export(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
                           float* records, t3d_stream stream);
 int t3d_tsdf_merge_records(t3d_tsdf* v, const float* records, int64_t b,
                            t3d_stream stream);
+/* The same two with the block count capped by *n_blocks_dev (device int32, nullable: no cap) — routing
+ * that overlaps fusion only looks at the blocks that existed after K4 of batch 0. */
+int t3d_tsdf_route_counts_upto(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
+                               int self_rank, const int32_t* n_blocks_dev, int32_t* counts,
+                               t3d_stream stream);
+int t3d_tsdf_route_export_upto(t3d_tsdf* v, int axis, int32_t slab_blocks, int world,
+                               int self_rank, const int32_t* n_blocks_dev,
+                               const int32_t* dst_base, int32_t* dst_fill, float* records,
+                               t3d_stream stream);
+/* Copy-engine routing (the default on one NVLink box): records are packed into a LOCAL send buffer
+ * (t3d_tsdf_route_export_upto), each destination's group is pushed into that owner's receive buffer with
+ * one t3d_memcpy_async (peer copy: NVLink through the copy engine, no SM involved) plus a 4-byte copy of
+ * the count, and after a barrier the owner merges every source's region with ONE call:
+ *   recv_base: [int32 count_from[world] | pad to header_bytes][region 0]...[region world-1],
+ *   region s = region_bytes bytes = up to region_records records from rank s (own rank: skipped).
+ * Blocks arriving from several sources are merged under a per-block lock. */
+int t3d_tsdf_merge_records_multi(t3d_tsdf* v, const void* recv_base, int64_t header_bytes,
+                                 int64_t region_bytes, int world, int self_rank,
+                                 int64_t region_records, t3d_stream stream);
 
 /* Fused export + transfer over peer memory (NVLink/NVSwitch): every non-owned block is stored
  * straight into its owner's receive region — peer_regions_h[d] is, in rank d's memory (opened
@@ -350,6 +371,8 @@ int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_ptr);
 int t3d_ipc_close(t3d_ctx* ctx, void* dev_ptr);
 int t3d_ipc_free(t3d_ctx* ctx, void* dev_ptr);
 int t3d_memset_async(void* dev_ptr, int value, size_t bytes, t3d_stream stream);
+/* cudaMemcpyAsync(cudaMemcpyDefault) between device buffers, peers included. */
+int t3d_memcpy_async(void* dst, const void* src, size_t bytes, t3d_stream stream);
 
 /* K6: surface points (R6).  xyz/nrm: cap*3 f32; rgb: cap*3 u8 (nullable
  * nrm/rgb).  out_n device int64.  Order: deterministic only as a set. */

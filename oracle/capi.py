@@ -59,6 +59,31 @@ def set_num_threads(n: int):
     lib().o_set_num_threads(C.c_int(n))
 
 
+def synth_frame(scene, i, H, W, fx, fy, cx, cy, seed=1234, noise_sigma=0.0):
+    """(depth f32 [H,W], bgr u8 [H,W,3], T_cw f64 [3,4]) — C/OpenMP twin of the synthetic scene generator
+    (same as textureless_3d_reconstruction_b200/synthetic.synth_frame, ~100x faster): the CPU arm of the
+    benchmark builds its workload with it, so that arm never loads the product library."""
+    if scene == 0:
+        yaw = np.deg2rad(2.0) * np.sin(0.03 * i)
+        o = np.array([0.1 * np.sin(0.05 * i), 0.0, 0.25 * i])
+    else:
+        yaw = np.deg2rad(0.5) * i
+        o = np.array([0.05 * i, 0.0, 0.0])
+    c, s = np.cos(yaw), np.sin(yaw)
+    R = np.ascontiguousarray(np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float64))
+    T = np.zeros((3, 4))
+    T[:, :3] = R.T
+    T[:, 3] = -R.T @ o
+    depth = np.empty((H, W), np.float32)
+    bgr = np.empty((H, W, 3), np.uint8)
+    seed32 = (seed ^ (seed >> 32)) & 0xFFFFFFFF
+    o = np.ascontiguousarray(o, np.float64)
+    lib().o_synth_frame(C.c_int(scene), C.c_int(i), C.c_int(H), C.c_int(W), C.c_double(fx), C.c_double(fy),
+                        C.c_double(cx), C.c_double(cy), C.c_uint32(seed32), C.c_float(noise_sigma), _p(R), _p(o),
+                        _p(depth), _p(bgr))
+    return depth, bgr, T
+
+
 def backproject(depth, bgr, fx, fy, cx, cy, scale=1.0, f64_mask=False, min_depth=0.1,
                 max_depth=50.0, pose=None, subsample=1):
     depth = np.ascontiguousarray(depth, np.float32)

@@ -1,5 +1,6 @@
-"""2+ GPU check (torchrun): the peer-memory router and the NCCL router leave bit-identical volumes,
-and both equal a single volume that fused every rank's frames (up to the merge's float rounding).
+"""2+ GPU check (torchrun): the copy-engine router, the peer-store router and the NCCL router leave
+bit-identical volumes, and all equal a single volume that fused every rank's frames (up to the merge's
+float rounding); routing underneath fusion (copy-engine and peer-store transports) equals routing after it.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_route_check.py
 """
@@ -30,28 +31,44 @@ def main():
     H, W, F = 240, 136, 12
     it = S.scaled_intrinsics(H, W)
     K = (it["fx"], it["fy"], it["cx"], it["cy"])
-    vols = [TSDFVolume(0.01, 0.04, block_capacity=120000, ctx=ctx) for _ in range(2)]
+    vols = [TSDFVolume(0.01, 0.04, block_capacity=120000, ctx=ctx) for _ in range(3)]
     for i in range(F):
         d, c, T = S.synth_frame(0, rank * F + i, H, W, *K, noise_sigma=0.002)
         for v in vols:
             v.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), K, T, 1.0, 5.0)
     a = D.BlockRouter(vols[0], rank, world, slab_frames=F, frame_advance=0.25, block_size=0.08)
     b = D.P2PBlockRouter(vols[1], rank, world, slab_frames=F, frame_advance=0.25, block_size=0.08, region_records=8192)
+    ce = D.CopyEngineBlockRouter(vols[2], rank, world, slab_frames=F, frame_advance=0.25, block_size=0.08,
+                                region_records=8192)
     def same():
         ea = by_key(*[x.cpu().numpy() for x in vols[0].export_blocks()])
         eb = by_key(*[x.cpu().numpy() for x in vols[1].export_blocks()])
-        good = vols[0].num_blocks == vols[1].num_blocks
-        for x, y in zip(ea, eb):
-            good = good and np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
-                                           y.view(np.uint32) if y.dtype == np.float32 else y)
+        ec = by_key(*[x.cpu().numpy() for x in vols[2].export_blocks()])
+        good = vols[0].num_blocks == vols[1].num_blocks == vols[2].num_blocks
+        for x, y, z in zip(ea, eb, ec):
+            bits = lambda q: q.view(np.uint32) if q.dtype == np.float32 else q  # noqa: E731
+            good = good and np.array_equal(bits(x), bits(y)) and np.array_equal(bits(x), bits(z))
         return good, eb
 
     a.route()
     b.route()
+    ce.route()
     torch.cuda.synchronize()
     sent, dropped = b.stats()
     ok, eb = same()
-    ok = ok and dropped == 0
+    ok = ok and dropped == 0 and ce.stats()[0] == sent
+    # a receive region that is too small raises before anything is sent (copy-engine transport)
+    from textureless_3d_reconstruction_b200._lib import T3DError
+    tiny = D.CopyEngineBlockRouter(TSDFVolume(0.01, 0.04, block_capacity=1000, ctx=ctx), rank, world, slab_frames=F,
+                                   frame_advance=0.25, block_size=0.08, region_records=4)
+    tiny.vol = vols[2]
+    raised = max(sent) <= 4
+    try:
+        tiny._read_counts(None)
+    except T3DError:
+        raised = True
+    ok = ok and raised
+    tiny.close()
     # owned region vs a serial fusion of all frames (weights exact, tsdf within the merge rounding)
     ref = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
     for r in range(world):
@@ -64,10 +81,10 @@ def main():
     ok2 = np.array_equal(eb[0][own], rk) and np.array_equal(eb[2][own], rw) and np.abs(eb[1][own] - rt).max() < 1e-4
     # route() does not drop the sender's copies, so routing again adds them a second time on the owner —
     # identically for both transports; this exercises the second receive buffer of the p2p router
-    a.route()
-    b.route()
-    a.route()
-    b.route()
+    for _ in range(2):
+        a.route()
+        b.route()
+        ce.route()
     torch.cuda.synchronize()
     ok = ok and same()[0] and b.stats()[1] == 0
     # ---- routing that overlaps fusion (tail batch first, merge before the head batch)
@@ -76,8 +93,11 @@ def main():
     dd = [torch.from_numpy(f[0]).cuda() for f in fr]
     cc = [torch.from_numpy(f[1]).cuda() for f in fr]
     vo = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
+    vc = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
     vs = TSDFVolume(0.01, 0.04, block_capacity=240000, ctx=ctx)
     ro = D.P2PBlockRouter(vo, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
+    rc = D.CopyEngineBlockRouter(vc, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08,
+                                 region_records=16384)
     rs = D.P2PBlockRouter(vs, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
     order = D.P2PBlockRouter.overlap_order(F2, B2)
     views_o = vo.make_frame_views([dd[i] for i in order], [cc[i] for i in order], [K] * F2, [fr[i][2] for i in order])
@@ -85,17 +105,22 @@ def main():
     ok3 = True
     for rep in range(3):                                   # both receive buffers, steady state
         vo.reset()
+        vc.reset()
         vs.reset()
         ro.fuse_overlapped(views_o, F2, H, W, B2, False, 1.0, 5.0)
+        rc.fuse_overlapped(views_o, F2, H, W, B2, False, 1.0, 5.0)
         vs.integrate_sequence(views_s, F2, H, W, B2, False, 1.0, 5.0)
         rs.route()
         torch.cuda.synchronize()
         lo2, hi2 = D.block_owner_range(rank, world, ro.slab_blocks)
         lo2, hi2 = max(lo2, -(1 << 20)), min(hi2, 1 << 20)
         eo = by_key(*[x.cpu().numpy() for x in vo.export_blocks_range(2, lo2, hi2)])
+        ec = by_key(*[x.cpu().numpy() for x in vc.export_blocks_range(2, lo2, hi2)])
         es = by_key(*[x.cpu().numpy() for x in vs.export_blocks_range(2, lo2, hi2)])
         ok3 = ok3 and np.array_equal(eo[0], es[0]) and np.array_equal(eo[2], es[2])      # keys, integer weights
         ok3 = ok3 and float(np.abs(eo[1] - es[1]).max()) < 1e-4 and ro.stats()[1] == 0 and ro.stats()[0] == rs.stats()[0]
+        ok3 = ok3 and np.array_equal(ec[0], eo[0]) and np.array_equal(ec[2], eo[2])      # copy-engine == peer-store
+        ok3 = ok3 and np.array_equal(ec[1].view(np.uint32), eo[1].view(np.uint32)) and rc.stats()[0] == ro.stats()[0]
     ref2 = TSDFVolume(0.01, 0.04, block_capacity=480000, ctx=ctx)
     for r in range(world):
         for i in range(F2):
@@ -106,12 +131,14 @@ def main():
     res = torch.tensor([int(ok), int(ok2), int(ok3)], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MGPU_ROUTE_CHECK p2p==nccl {bool(res[0].item())} owned==serial {bool(res[1].item())} "
+        print(f"MGPU_ROUTE_CHECK ce==p2p==nccl {bool(res[0].item())} owned==serial {bool(res[1].item())} "
               f"overlapped==serial {bool(res[2].item())} sent_rank0={sent} overlapped_sent_rank0={ro.stats()[0]} "
               f"blocks_rank0={vols[1].num_blocks}", flush=True)
     ro.close()
+    rc.close()
     rs.close()
     b.close()
+    ce.close()
     dist.destroy_process_group()
     sys.exit(0 if res.min().item() == 1 else 1)
 

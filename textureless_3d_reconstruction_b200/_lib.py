@@ -62,7 +62,7 @@ _lib = None
 
 # name -> (restype, argtypes)
 _VP, _I, _I64, _D, _F = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
-SEQUENCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)  # t3d_sequence_hook(user, event)
+SEQUENCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)  # t3d_sequence_hook(user, touch_event, event)
 
 _SIGS = {
     "t3d_last_error": (C.c_char_p, []),
@@ -97,6 +97,10 @@ _SIGS = {
     "t3d_tsdf_route_counts": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP]),
     "t3d_tsdf_route_export": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _VP, _VP]),
     "t3d_tsdf_merge_records": (_I, [_VP, _VP, _I64, _VP]),
+    "t3d_tsdf_route_counts_upto": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _VP]),
+    "t3d_tsdf_route_export_upto": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "t3d_tsdf_merge_records_multi": (_I, [_VP, _VP, _I64, _I64, _I, _I, _I64, _VP]),
+    "t3d_memcpy_async": (_I, [_VP, _VP, C.c_size_t, _VP]),
     "t3d_tsdf_route_export_p2p": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _I64, _VP, _VP, _VP]),
     "t3d_tsdf_integrate_sequence_hooked": (_I, [_VP, C.POINTER(FrameView), _I, _I, _I, _I, _I, _F, _F, _VP,
                                                 SEQUENCE_HOOK, _VP, _VP, _VP]),

@@ -65,7 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (obj_dir / "ptxas.log").write_text("\n".join(log_lines))
     if verbose:
         print("\n".join(log_lines))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
+    # the link step gets the same -gencode: without it nvcc emits a stub for its default (sm_52) target
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB_PATH
 

@@ -897,12 +897,9 @@ static int bp_launch(t3d_ctx* ctx, const t3d_backproject_params* q, const BPFram
     const dim3 sgrid(p.num_tiles < want ? p.num_tiles : want), sblock(ST_THREADS);
 #define ST_LAUNCH(M, F)                                                                              \
   do {                                                                                               \
-    static bool attr_done = false;                                                                   \
-    if (!attr_done) {                                                                                \
+    if (ctx->func_attr_needed(reinterpret_cast<const void*>(&backproject_stream_kernel<M, F>)))      \
       T3D_CUDA(cudaFuncSetAttribute(backproject_stream_kernel<M, F>,                                 \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));    \
-      attr_done = true;                                                                              \
-    }                                                                                                \
     backproject_stream_kernel<M, F><<<sgrid, sblock, ST_SMEM_BYTES, st>>>(p);                        \
   } while (0)
     if (q->rgb_out_f32) {
@@ -964,6 +961,7 @@ extern "C" int t3d_backproject(t3d_ctx* ctx, const void* depth, const uint8_t* b
                                void* out_rgb, int64_t capacity, int64_t* out_n,
                                t3d_stream stream) {
   T3D_REQUIRE(ctx && q && out_n, "t3d_backproject: null ctx/params/out_n");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_REQUIRE(!q->has_color || bgr, "t3d_backproject: has_color but bgr is NULL");
   cudaStream_t st = as_stream(stream);
   int64_t P64 = 0;
@@ -996,6 +994,7 @@ extern "C" int t3d_backproject_batch(t3d_ctx* ctx, const t3d_backproject_frame* 
                                      int64_t* out_offsets, t3d_stream stream) {
   T3D_REQUIRE(ctx && q && out_offsets && (n_frames == 0 || frames_h),
               "t3d_backproject_batch: null argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_REQUIRE(n_frames >= 0, "t3d_backproject_batch: n_frames < 0");
   cudaStream_t st = as_stream(stream);
   int64_t P64 = 0;

@@ -105,6 +105,16 @@ struct t3d_ctx {
     cudaGraphExec_t exec = nullptr;
   };
   std::vector<CachedGraph> graphs;
+  // one-time per-DEVICE initialisation (constant-memory tables, cudaFuncSetAttribute opt-ins): kept here,
+  // not in function-local statics — a process may hold one ctx per GPU and both are per device
+  bool icp_offsets_ready = false;
+  std::vector<const void*> func_attrs_done;
+  bool func_attr_needed(const void* fn) {
+    for (const void* f : func_attrs_done)
+      if (f == fn) return false;
+    func_attrs_done.push_back(fn);
+    return true;
+  }
 };
 
 // host-side phase timing, printed to stderr when T3D_TRACE is set (debug aid)

@@ -113,13 +113,22 @@ extern "C" int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_pt
 
 extern "C" int t3d_ipc_close(t3d_ctx* ctx, void* dev_ptr) {
   T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_close: bad argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_CUDA(cudaIpcCloseMemHandle(dev_ptr));
   return T3D_OK;
 }
 
 extern "C" int t3d_ipc_free(t3d_ctx* ctx, void* dev_ptr) {
   T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_free: bad argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_CUDA(cudaFree(dev_ptr));
+  return T3D_OK;
+}
+
+// Device-to-device copy on the copy engine (also between peers mapped with t3d_ipc_open: NVLink, no SM work)
+extern "C" int t3d_memcpy_async(void* dst, const void* src, size_t bytes, t3d_stream stream) {
+  T3D_REQUIRE((dst && src) || bytes == 0, "t3d_memcpy_async: null pointer");
+  if (bytes) T3D_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
   return T3D_OK;
 }
 

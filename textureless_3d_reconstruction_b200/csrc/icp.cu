@@ -622,8 +622,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   int rc;
   if ((rc = ctx->scratch[0].reserve(hc * 36)) != T3D_OK) return rc;
   if ((rc = ctx->scratch[1].reserve((size_t)n_tgt * 28 + 64)) != T3D_OK) return rc;
-  static bool ofs_ready = false;
-  if (!ofs_ready) {  // 5^3 offsets sorted by (ring, squared length)
+  if (!ctx->icp_offsets_ready) {  // 5^3 offsets sorted by (ring, squared length)
     signed char h_ofs[125][4];
     int order[125], key[125];
     for (int i = 0; i < 125; ++i) {
@@ -640,7 +639,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
       h_ofs[i][2] = (signed char)(o / 25 - 2); h_ofs[i][3] = 0;
     }
     T3D_CUDA(cudaMemcpyToSymbol(c_ofs, h_ofs, sizeof(h_ofs)));
-    ofs_ready = true;
+    ctx->icp_offsets_ready = true;
   }
   HGrid g;
   g.keys = ctx->scratch[0].as<unsigned long long>();
@@ -778,6 +777,7 @@ extern "C" int t3d_icp_linearize(t3d_ctx* ctx, const float* src, int64_t n_src, 
                                  const double* T_h, double* out27_h, double* out_stats_h,
                                  t3d_stream stream) {
   T3D_REQUIRE(ctx && T_h && out27_h && out_stats_h, "t3d_icp_linearize: null argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_REQUIRE(max_corr_dist > 0.0, "t3d_icp_linearize: max_corr_dist must be > 0");
   for (int k = 0; k < 27; ++k) out27_h[k] = 0.0;
   out_stats_h[0] = out_stats_h[1] = 0.0;
@@ -802,6 +802,7 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
                                       double rel_fitness, double rel_rmse,
                                       t3d_icp_result* res, t3d_stream stream) {
   T3D_REQUIRE(ctx && res, "t3d_icp_point_to_plane: null argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_REQUIRE(max_corr_dist > 0.0 && max_iter >= 0, "t3d_icp_point_to_plane: bad parameters");
   memset(res, 0, sizeof(*res));
   for (int i = 0; i < 16; ++i) res->T[i] = T0_h ? T0_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);
@@ -820,6 +821,7 @@ extern "C" int t3d_icp_point_to_plane_dev(t3d_ctx* ctx, const float* src, int64_
                                           int* skipped_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && res && src && tgt && tgt_nrm && n_src_dev && n_tgt_dev && src_capacity > 0 && tgt_capacity > 0,
               "t3d_icp_point_to_plane_dev: null argument");
+  T3D_CUDA(cudaSetDevice(ctx->device));
   T3D_REQUIRE(max_corr_dist > 0.0 && max_iter >= 0, "t3d_icp_point_to_plane_dev: bad parameters");
   memset(res, 0, sizeof(*res));
   for (int i = 0; i < 16; ++i) res->T[i] = T0_h ? T0_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);

@@ -192,6 +192,12 @@ class DepthEnhancedReconstruction:
             if depth is None:
                 continue
             d = torch.from_numpy(np.ascontiguousarray(depth, np.float32)).to(dev)
+            if img.shape[:2] != (h, w):
+                raise ValueError(f"image {i} is {img.shape[:2]}, the first image is {(h, w)}")
+            if tuple(d.shape) != (h, w):
+                # the reference's estimate() resizes the network output to the image (der:157-166); depth files of
+                # another size get the same treatment as d2r:465-467 (cv2.INTER_LINEAR semantics, on the GPU)
+                d = ctx.resize_bilinear(d, h, w)
             c = torch.from_numpy(np.ascontiguousarray(img, np.uint8)).to(dev)
             T_cw = tracker.add_frame(d, c, init_pose=None if init_poses is None else init_poses[i])
             if tracker.icp_log[-1] is not None:

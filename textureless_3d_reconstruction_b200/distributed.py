@@ -246,7 +246,7 @@ class P2PBlockRouter:
             self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
         side = self._side
 
-        def after_batch0(ev):
+        def after_batch0(_ev_touch, ev):
             h = C.c_void_p(side.cuda_stream)
             _lib.check(self.lib.t3d_stream_wait_event(h, ev))
             with torch.cuda.stream(side):
@@ -258,9 +258,16 @@ class P2PBlockRouter:
         _lib.check(self.lib.t3d_stream_wait_event(_stream(), self._done))
 
     def stats(self):
-        """(records sent per destination, records that did not fit) of the last route — synchronises."""
+        """(records sent per destination, records that did not fit) of the last route — synchronises, and
+        raises if the export kernel had to drop records (the counters live on the device: this transport
+        never syncs on its own, so callers check here, at their next host sync)."""
+        from . import _lib
         f = self.fill.cpu().tolist()
         sent = [f[d] if d != self.rank else 0 for d in range(self.world)]
+        if f[self.world + 1] != 0:
+            raise _lib.T3DError(_lib.T3D_E_CAPACITY,
+                                f"P2PBlockRouter: {f[self.world + 1]} block records did not fit the receive regions "
+                                f"(region_records={self.region_records}); the fused volume is incomplete")
         return sent, f[self.world + 1]
 
     def close(self):
@@ -273,6 +280,137 @@ class P2PBlockRouter:
                     self.lib.t3d_ipc_close(self.ctx.handle, self.peers[parity][d])
             self.lib.t3d_ipc_free(self.ctx.handle, self.local[parity])
         self.peers, self.local = [], []
+
+class CopyEngineBlockRouter(P2PBlockRouter):
+    """Block routing with the transfer on the COPY ENGINE (default on one NVLink box).  K5's persistent CTAs
+    own every SM while a step runs, so an export kernel that stores 114 MB per rank over NVLink holds SMs for
+    as long as the link takes; here the SMs only pack the records into a local send buffer (an HBM-speed
+    copy), each destination's group then travels with ONE peer cudaMemcpyAsync (NVLink through the copy
+    engine, concurrent with fusion) plus a 4-byte copy of its count, a 4-byte NCCL all_reduce orders
+    "all copies done" before "merge", and ONE fused launch merges every source's region.
+
+    The per-destination counts are read on the host (the copies need their sizes): in the overlapped mode
+    that read waits only for K4 of batch 0 — all blocks that will travel exist from then on — i.e. it returns
+    while K5 of batch 0 is still running, so fusion never waits for it.  Knowing the counts on the host also
+    means a receive region that is too small raises immediately instead of dropping records."""
+
+    def __init__(self, vol, rank, world, slab_frames, frame_advance, block_size, region_records=16384, group=None):
+        import torch
+        super().__init__(vol, rank, world, slab_frames, frame_advance, block_size, region_records, group)
+        dev = self.ctx.device
+        self.counts_dev = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.base_dev = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.fill_dev = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.counts_pin = torch.zeros(world, dtype=torch.int32).pin_memory()
+        self.base_pin = torch.zeros(world, dtype=torch.int32).pin_memory()
+        self.send = None
+        self.last_counts = [0] * world
+        self.route_events = []          # (start, end) CUDA events of every route, for bench.py
+
+    def _read_counts(self, n_blocks_dev):
+        """Enqueue the per-owner count on the current stream and read it on the host."""
+        import torch
+        from . import _lib
+        from .runtime import _ptr, _stream
+        _lib.check(self.lib.t3d_tsdf_route_counts_upto(self.vol.handle, self.AXIS, self.slab_blocks, self.world, self.rank,
+                                                       _ptr(n_blocks_dev), _ptr(self.counts_dev), _stream()))
+        self.counts_pin.copy_(self.counts_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        counts = self.counts_pin.tolist()
+        worst = max(counts)
+        if worst > self.region_records:
+            raise _lib.T3DError(_lib.T3D_E_CAPACITY,
+                                f"CopyEngineBlockRouter: {worst} block records for one owner exceed the receive region "
+                                f"(region_records={self.region_records}); nothing was sent — raise region_records")
+        return counts
+
+    def _send(self, counts, n_blocks_dev):
+        """pack -> per-destination peer copies -> fence -> merge, all on the current stream."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .runtime import _ptr, _stream
+        par = self.step & 1
+        self.step += 1
+        total = sum(counts)
+        rec_bytes = self.vol.RECORD_WORDS * 4
+        if total > 0:
+            if self.send is None or self.send.shape[0] < total:
+                self.send = torch.empty((int(total * 1.25) + 16, self.vol.RECORD_WORDS), dtype=torch.float32,
+                                        device=self.ctx.device)
+            base, acc = [], 0
+            for c in counts:
+                base.append(acc)
+                acc += c
+            self.base_pin.copy_(torch.tensor(base, dtype=torch.int32))
+            self.base_dev.copy_(self.base_pin, non_blocking=True)
+            _lib.check(self.lib.t3d_tsdf_route_export_upto(self.vol.handle, self.AXIS, self.slab_blocks, self.world,
+                                                           self.rank, _ptr(n_blocks_dev), _ptr(self.base_dev),
+                                                           _ptr(self.fill_dev), _ptr(self.send), _stream()))
+            for d, c in enumerate(counts):
+                if d == self.rank or c == 0:
+                    continue
+                _lib.check(self.lib.t3d_memcpy_async(self._regions[par][d], C.c_void_p(self.send.data_ptr() + base[d] * rec_bytes),
+                                                     c * rec_bytes, _stream()))
+                _lib.check(self.lib.t3d_memcpy_async(self._counts[par][d], C.c_void_p(self.counts_dev.data_ptr() + 4 * d),
+                                                     4, _stream()))
+        dist.all_reduce(self.token, group=self.group)     # every rank's copies precede every rank's merge
+        local = self.local[par]
+        _lib.check(self.lib.t3d_tsdf_merge_records_multi(self.vol.handle, C.c_void_p(local), self.HEADER, self.region_bytes,
+                                                         self.world, self.rank, self.region_records, _stream()))
+        _lib.check(self.lib.t3d_memset_async(C.c_void_p(local), 0, self.HEADER, _stream()))
+        self.last_counts = counts
+
+    def route(self, n_blocks_dev=None):
+        import torch
+        if self.world == 1:
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._send(self._read_counts(n_blocks_dev), n_blocks_dev)
+        e1.record()
+        self.route_events.append((e0, e1))
+
+    def fuse_overlapped(self, views_reordered, n_frames, H, W, batch, depth_is_u16=False, depth_scale=1.0,
+                        depth_max=5.0, frame_advance=0.25):
+        import torch
+        from . import _lib
+        from .runtime import _stream
+        nb = -(-n_frames // batch)
+        reach = int(np.ceil(depth_max / frame_advance)) + 2
+        if nb < 3 or batch < reach:
+            raise ValueError(f"overlapped routing needs >= 3 batches of >= {reach} frames (got {nb} x {batch})")
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.ctx.device)
+            self._done = C.c_void_p()
+            _lib.check(self.lib.t3d_event_create(C.byref(self._done)))
+            self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        side = self._side
+
+        def after_batch0(ev_touch, ev):
+            h = C.c_void_p(side.cuda_stream)
+            with torch.cuda.stream(side):
+                # the blocks that will travel exist once K4 of batch 0 is done: count them (host read) while
+                # K5 of batch 0 is still running ...
+                _lib.check(self.lib.t3d_stream_wait_event(h, ev_touch))
+                counts = self._read_counts(self._snap)
+                # ... and pack / copy / merge behind K5 of batch 0, underneath the fusion of the middle batches
+                _lib.check(self.lib.t3d_stream_wait_event(h, ev))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._send(counts, self._snap)
+                e1.record()
+                self.route_events.append((e0, e1))
+            _lib.check(self.lib.t3d_event_record(self._done, h))
+
+        self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, after_batch0,
+                                           self._done, depth_is_u16, depth_scale, depth_max)
+        _lib.check(self.lib.t3d_stream_wait_event(_stream(), self._done))
+
+    def stats(self):
+        """(records sent per destination, records dropped = always 0: an overflow raises before anything is sent)."""
+        return [c if d != self.rank else 0 for d, c in enumerate(self.last_counts)], 0
+
 
 
 def allreduce_normal_equations(acc27, sum_d2, count, device=None, group=None):

@@ -45,6 +45,26 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _check_frame(depth, bgr=None, conf_mask=None, what="frame"):
+    """The kernels index colour / confidence with the depth map's H and W: a mismatch would read out of
+    bounds on the device (the reference raises IndexError there), so it is rejected here — with real
+    exceptions, not asserts, which vanish under python -O."""
+    torch = _torch()
+    if depth.dim() != 2 or not depth.is_cuda or not depth.is_contiguous():
+        raise ValueError(f"{what}: depth must be a contiguous (H, W) CUDA tensor, got {tuple(depth.shape)}")
+    H, W = depth.shape
+    if bgr is not None:
+        if tuple(bgr.shape) != (H, W, 3) or bgr.dtype != torch.uint8 or not bgr.is_cuda or not bgr.is_contiguous():
+            raise ValueError(f"{what}: colour must be a contiguous uint8 CUDA tensor of shape {(H, W, 3)} matching the "
+                             f"depth map, got {tuple(bgr.shape)} {bgr.dtype}")
+    if conf_mask is not None:
+        if tuple(conf_mask.shape) != (H, W) or conf_mask.dtype != torch.uint8 or not conf_mask.is_cuda \
+                or not conf_mask.is_contiguous():
+            raise ValueError(f"{what}: conf_mask must be a contiguous uint8 CUDA tensor of shape {(H, W)}, "
+                             f"got {tuple(conf_mask.shape)} {conf_mask.dtype}")
+    return H, W
+
+
 def _np_ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -166,9 +186,9 @@ class Context:
         Returns (xyz[cap,3] f32, rgb[cap,3] u8|f32 or None, n int64[1]) — all on device;
         only the first n rows are valid."""
         torch = _torch()
-        H, W = depth.shape
-        assert depth.is_cuda and depth.is_contiguous()
-        assert depth.dtype in (torch.float32, torch.float64)
+        H, W = _check_frame(depth, bgr, conf_mask, "backproject")
+        if depth.dtype not in (torch.float32, torch.float64):
+            raise ValueError(f"backproject: depth must be float32 or float64, got {depth.dtype}")
         p = BackprojectParams()
         p.H, p.W, p.subsample = H, W, int(subsample)
         p.depth_is_f64 = int(depth.dtype == torch.float64)
@@ -192,8 +212,6 @@ class Context:
                                   device=depth.device)
         if out_n is None:
             out_n = torch.zeros(1, dtype=torch.int64, device=depth.device)
-        if bgr is not None:
-            assert bgr.is_cuda and bgr.is_contiguous() and bgr.dtype == torch.uint8
         check(self.lib.t3d_backproject(self.handle, _ptr(depth), _ptr(bgr), _ptr(conf_mask), C.byref(p),
                                        _ptr(out_xyz), _ptr(out_rgb), out_xyz.shape[0], _ptr(out_n), _stream()))
         return out_xyz, out_rgb, out_n
@@ -203,6 +221,10 @@ class Context:
         n = len(depths)
         arr = (BackprojectFrame * n)()
         for i in range(n):
+            _check_frame(depths[i], bgrs[i] if bgrs is not None else None,
+                         conf_masks[i] if conf_masks is not None else None, f"backproject frame {i}")
+            if depths[i].shape != depths[0].shape or depths[i].dtype != depths[0].dtype:
+                raise ValueError("backproject_batch: every frame of a batch must have the same size and dtype")
             arr[i].depth = depths[i].data_ptr()
             arr[i].bgr = bgrs[i].data_ptr() if bgrs is not None and bgrs[i] is not None else None
             arr[i].conf_mask = conf_masks[i].data_ptr() if conf_masks is not None and conf_masks[i] is not None else None
@@ -525,6 +547,9 @@ class TSDFVolume:
         n = len(depths)
         arr = (FrameView * n)()
         for i in range(n):
+            _check_frame(depths[i], bgrs[i] if bgrs is not None else None, None, f"TSDF frame {i}")
+            if depths[i].shape != depths[0].shape or depths[i].dtype != depths[0].dtype:
+                raise ValueError("TSDF integration: every frame of a batch must have the same size and dtype")
             arr[i].depth = depths[i].data_ptr()
             arr[i].bgr = bgrs[i].data_ptr() if bgrs is not None and bgrs[i] is not None else None
             K = np.asarray(Ks[i] if isinstance(Ks, (list, tuple)) else Ks, np.float32).reshape(4)
@@ -551,14 +576,15 @@ class TSDFVolume:
                                   depth_is_u16=False, depth_scale=1.0, depth_max=5.0, start=0):
         """integrate_sequence with the routing hooks of t3d_tsdf_integrate_sequence_hooked:
         nblocks_dev (int32[1] CUDA tensor) receives the block count after K4 of batch 0,
-        after_batch0(event_handle) is called on the host once K5 of batch 0 is enqueued, and the
+        after_batch0(touch_event_handle, event_handle) is called on the host once K5 of batch 0 is enqueued
+        (the first event completes with K4 of batch 0, the second with K5 of batch 0), and the
         last batch waits for wait_event (a handle from t3d_event_create)."""
         sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
         err = []
 
-        def _cb(_user, ev):
+        def _cb(_user, ev_touch, ev):
             try:
-                after_batch0(C.c_void_p(ev))
+                after_batch0(C.c_void_p(ev_touch), C.c_void_p(ev))
             except BaseException as e:  # noqa: BLE001 - must not propagate through the C frame
                 err.append(e)
         cb = _lib.SEQUENCE_HOOK(_cb)

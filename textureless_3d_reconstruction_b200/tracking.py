@@ -126,6 +126,9 @@ class FrameToModelTracker:
         bgr (H,W,3) u8 are CUDA tensors.  Returns the frame's world->camera 4x4."""
         import time
         torch = __import__("torch")
+        from .runtime import _check_frame
+        if _check_frame(depth, bgr, None, "add_frame") != (self.H, self.W):
+            raise ValueError(f"add_frame: frame is {tuple(depth.shape)}, the tracker was built for {(self.H, self.W)}")
         caller = torch.cuda.current_stream()
         self.stream.wait_stream(caller)                 # the frame was produced on the caller's stream
         depth.record_stream(self.stream)
