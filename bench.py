@@ -41,15 +41,29 @@ METRIC = "RGB-D frames fused/sec @1080x1920 (TSDF integration, cfg2)"
 UNIT = "frames/s"
 
 
+def kernel_source_sha():
+    """sha256 of the file that holds the dominant kernel: profiles/*_k5_traffic.json records it at capture time."""
+    import hashlib
+    return hashlib.sha256((ROOT / "textureless_3d_reconstruction_b200" / "csrc" / "tsdf.cu").read_bytes()).hexdigest()
+
+
 def load_traffic():
-    """DRAM bytes per K5 launch from the committed `ncu --set full` capture of this same
-    command (profiles/r1_k5_traffic.json, written by profiles/summarize_ncu.py traffic)."""
-    p = ROOT / "profiles" / "r1_k5_traffic.json"
-    try:
-        d = json.loads(p.read_text())
-        return float(d["dram_bytes_per_launch"]), d
-    except Exception:  # noqa: BLE001
-        return None, None
+    """DRAM bytes per K5 launch from the newest committed `ncu --set full` capture of this command
+    (profiles/r*_k5_traffic.json, written by profiles/summarize_ncu.py traffic).  The capture records the
+    sha256 of csrc/tsdf.cu; if the kernel source has changed since, the number is NOT replayed:
+    `traffic` is null and `traffic_stale` says why."""
+    cands = sorted((ROOT / "profiles").glob("r*_k5_traffic.json"), reverse=True)
+    for p in cands:
+        try:
+            d = json.loads(p.read_text())
+        except Exception:  # noqa: BLE001
+            continue
+        d["file"] = p.name
+        if d.get("kernel_source_sha256") == kernel_source_sha():
+            return float(d["dram_bytes_per_launch"]), d, None
+        return None, d, (f"{p.name} was captured for another version of csrc/tsdf.cu "
+                         f"(sha256 {str(d.get('kernel_source_sha256'))[:12]} != {kernel_source_sha()[:12]}); re-run profiles/capture.sh")
+    return None, None, "no capture committed"
 
 
 def load_peaks():
@@ -117,16 +131,58 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------- reference arm
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def oracle_frames(n, first=0):
+    """cfg frames [first, first+n) from the ORACLE's own generator (oracle/t3d_oracle.c:o_synth_frame, the C twin
+    of the device generator) — the reference arm never loads the product library.  Cached under /tmp between
+    the driver's back-to-back reference runs."""
+    from oracle import capi
+    cache = Path(os.environ.get("T3D_BENCH_CACHE", "/tmp/t3d_bench_frames"))
+    tag = f"{H}x{W}_{KINTR[0]:g}_{SEED}_{NOISE:g}"
+    out = []
+    for i in range(first, first + n):
+        fd, fc = cache / f"{tag}_{i:05d}_d.npy", cache / f"{tag}_{i:05d}_c.npy"
+        d = c = None
+        try:
+            if fd.exists() and fc.exists():
+                d, c = np.load(fd), np.load(fc)
+        except Exception:  # noqa: BLE001
+            d = c = None
+        T = None
+        if d is None or d.shape != (H, W):
+            d, c, T = capi.synth_frame(0, i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE)
+            try:
+                cache.mkdir(parents=True, exist_ok=True)
+                np.save(fd, d)
+                np.save(fc, c)
+            except Exception:  # noqa: BLE001
+                pass
+        if T is None:
+            from textureless_3d_reconstruction_b200 import synthetic as S
+            T = S.scene_pose(0, i)[2]
+        out.append((d, c, T))
+    return out
+
+
 def run_reference(args):
-    """CPU arm: the oracle (C/OpenMP restatement of the same TSDF semantics — the reference
-    has no TSDF code and is pure Python, so nothing compiles into oracle/_ref) on all host
-    cores, each step a bounded sample of the same workload."""
+    """CPU arm: the oracle (C/OpenMP restatement of the same TSDF semantics — the reference has no TSDF code
+    and is pure Python, so nothing compiles into oracle/_ref) on ALL host cores (torchrun exports
+    OMP_NUM_THREADS=1: overridden), each step a bounded sample of the same workload.  Only `oracle/` and the
+    pure-Python pose helper are loaded: no libt3d.so, no CUDA."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     from oracle import capi
-    frames = make_host_frames(args.cpu_frames, first=0)
-    cores = capi.num_threads()
+    cores = host_threads()
+    capi.set_num_threads(cores)
+    n = min(args.ref_frames, args.frames)
+    frames = oracle_frames(n, first=0)
 
     def step():
         ov = capi.TSDFVolume(VOXEL, TRUNC)
@@ -141,42 +197,23 @@ def run_reference(args):
         ov = step()
     dt = time.perf_counter() - t0
     fps = args.steps * len(frames) / dt
-    sample = (f"frames 0..{len(frames) - 1} of the workload's frames per step (new volume + touch + integrate), "
-              f"oracle/t3d_oracle.c, {cores} OpenMP threads")
+    sample = (f"frames 0..{len(frames) - 1} of the workload's {args.frames} frames per step and GPU (new volume + touch + "
+              f"integrate), oracle/t3d_oracle.c, {capi.num_threads()} OpenMP threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (tunnel T1, seed 1234; frames generated once, outside the timed region)",
-        "config": workload_config(len(frames), 1),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic (tunnel T1, sigma=2 mm depth noise, seed 1234; generated on the host by the oracle's C twin "
+                "of the device generator, outside the timed region)",
+        "config": workload_config(args.frames, args.gpus),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": capi.num_threads(), "kind": "port", "sample": sample,
+                         "frames_source": "oracle/t3d_oracle.c:o_synth_frame (C twin of the device generator; depths "
+                                          "agree with it to ~1e-6 m)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "blocks": int(ov.num_blocks),
+        "blocks": int(ov.num_blocks), "voxel_updates": ov.counters()["voxel_updates"],
     }
     print(json.dumps(line), flush=True)
-
-
-def make_host_frames(n, first=0):
-    """Host copies of cfg2 frames [first, first+n): device generator when a GPU is there
-    (data creation only), NumPy twin otherwise."""
-    try:
-        import torch
-        has_gpu = torch.cuda.is_available()
-    except Exception:  # noqa: BLE001
-        has_gpu = False
-    out = []
-    if has_gpu:
-        from textureless_3d_reconstruction_b200.runtime import get_context
-        ctx = get_context(0)
-        for i in range(first, first + n):
-            d, c, T = ctx.synth_frame(0, i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE)
-            out.append((d.cpu().numpy(), c.cpu().numpy(), T))
-    else:
-        from textureless_3d_reconstruction_b200 import synthetic as S
-        for i in range(first, first + n):
-            out.append(S.synth_frame(0, i, H, W, *KINTR, seed=SEED, noise_sigma=NOISE))
-    return out
 
 
 WORKLOAD_NAME = ("BASELINE configs[1]: TSDF integration, 300 synthetic 1080x1920 frames, 1 cm voxels, "
@@ -221,15 +258,16 @@ def run_ours(args):
 
     router = None
     if world > 1:
-        from textureless_3d_reconstruction_b200.distributed import BlockRouter, P2PBlockRouter
-        if args.router == "p2p":
-            router = P2PBlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8,
-                                    region_records=args.region_records)
+        from textureless_3d_reconstruction_b200.distributed import BlockRouter, CopyEngineBlockRouter, P2PBlockRouter
+        if args.router in ("ce", "p2p"):
+            cls = CopyEngineBlockRouter if args.router == "ce" else P2PBlockRouter
+            router = cls(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8,
+                         region_records=args.region_records)
         else:
             router = BlockRouter(vol, rank, world, slab_frames=F, frame_advance=0.25, block_size=VOXEL * 8)
 
     route_events = []
-    overlap = (router is not None and args.router == "p2p" and not args.no_overlap and not args.serial_batches
+    overlap = (router is not None and args.router in ("ce", "p2p") and not args.no_overlap and not args.serial_batches
                and -(-F // B) >= 3 and B >= int(np.ceil(DEPTH_MAX / 0.25)) + 2)
     views_ov = None
     if overlap:
@@ -265,6 +303,8 @@ def run_ours(args):
         step()
     barrier()
     route_events.clear()
+    if hasattr(router, "route_events"):
+        router.route_events.clear()
 
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local)
@@ -292,6 +332,47 @@ def run_ours(args):
     total_frames = F * world * args.steps
     fps = total_frames / (ms * 1e-3)
 
+    # ---- N > 1: routing report + conservation check on EVERY rank (not only rank 0)
+    routing = None
+    if router is not None:
+        if args.router in ("ce", "p2p"):
+            sent, dropped = router.stats()          # raises if a transport had to drop records
+            revs = router.route_events if hasattr(router, "route_events") else route_events
+            route_ms = float(np.mean([a.elapsed_time(b) for a, b in revs])) if revs else None
+            transport = ("pack kernel into a local send buffer, ONE peer cudaMemcpyAsync per destination (NVLink through "
+                         "the copy engine, no SM work) + 4-byte count copy, 4-byte NCCL all_reduce as the copy->merge "
+                         "fence, one fused merge launch for all sources" if args.router == "ce" else
+                         "export kernel stores 10 KiB block records straight into the owner's memory over NVLink (CUDA "
+                         "IPC peer mapping); 4-byte NCCL all_reduce as the export->merge fence; owner merges from its own HBM")
+            routing = {"blocks_sent_rank0": int(sum(sent)), "records_dropped_rank0": int(dropped),
+                       "bytes_sent_rank0": int(sum(sent)) * 4 * vol.RECORD_WORDS, "route_ms_per_step_rank0": route_ms,
+                       "route_ms_note": "CUDA events on the router's stream around count/pack/copies/fence/merge"
+                                        + (" (runs underneath fusion)" if overlap else ""),
+                       "overlapped_with_fusion": bool(overlap),
+                       "batch_order": ("last batch (frames that reach past the slab) first, routing on a side "
+                                       "stream underneath the other batches, first batch last after the merge"
+                                       if overlap else "ascending, routing after fusion"),
+                       "transport": transport}
+        else:
+            dropped = 0
+            routing = {"blocks_sent_rank0": router.last_sent, "blocks_received_rank0": router.last_received,
+                       "bytes_sent_rank0": router.last_sent * 4 * router.RECORD,
+                       "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
+                       "transport": "NCCL all_to_all_single (counts) + all_to_all_single (10 KiB block records)"}
+        # conservation: every voxel update of every rank must end up, exactly once, as one unit of weight in a block
+        # of the rank that OWNS it:  sum_ranks sum(weights of owned blocks) == sum_ranks voxel_updates
+        from textureless_3d_reconstruction_b200.distributed import block_owner_range
+        lo, hi = block_owner_range(rank, world, router.slab_blocks)
+        _, _, w_owned, _ = vol.export_blocks_range(2, max(lo, -(1 << 20)), min(hi, 1 << 20))
+        t = torch.tensor([float(w_owned.double().sum().item()), float(cnt["voxel_updates"]), float(dropped)],
+                         dtype=torch.float64, device=dev)
+        del w_owned
+        dist.all_reduce(t)
+        assert int(t[2].item()) == 0, "block records were dropped on some rank: raise --region-records"
+        assert int(t[0].item()) == int(t[1].item()), f"routing lost or duplicated weight: owned {t[0].item()} != updates {t[1].item()}"
+        routing["conservation"] = {"sum_owned_weights_all_ranks": int(t[0].item()), "sum_voxel_updates_all_ranks": int(t[1].item()),
+                                   "records_dropped_all_ranks": 0, "checked": True}
+
     # ---- roofline of the dominant kernel (K5 integrate), per launch
     peak, peak_src = load_peaks()
     calls_per_step = -(-F // B)
@@ -300,11 +381,12 @@ def run_ours(args):
     k5_ms_per_launch = prof["integrate_ms"] / max(prof["calls"], 1)
     k4_ms_per_launch = prof["touch_ms"] / max(prof["calls"], 1)
     achieved = (alg_bytes_step / calls_per_step) / (k5_ms_per_launch * 1e-3) / 1e9
-    traffic, tinfo = load_traffic() if args.workload == "cfg2" else (None, None)
+    traffic, tinfo, tstale = load_traffic() if args.workload == "cfg2" else (None, None, "captured for cfg2 only")
     traffic_src = None if tinfo is None else tinfo.get("source")
     roofline = {
         "kernel": "integrate_kernel (K5)", "bound": "hbm", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "traffic_stale": tstale,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_step / calls_per_step,
         "avg_launch_ms": k5_ms_per_launch, "launches_timed": prof["calls"],
@@ -331,7 +413,18 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args, depth_all, bgr_all, poses)
+        cpu = cpu_baseline(args, depth_all, bgr_all, poses, cnt, nblocks)
+
+    # ---- secondary workloads (short fixed-size runs of the other BASELINE configs, each with its CPU oracle number)
+    secondary = {}
+    if not args.no_secondary and args.workload == "cfg2":
+        del depth_all, bgr_all, views
+        torch.cuda.empty_cache()
+        if world == 1:
+            secondary["cfg3"] = guarded(lambda: secondary_cfg3(args, ctx))
+            secondary["cfg1"] = guarded(lambda: secondary_cfg1(args, ctx))
+        else:
+            secondary["cfg5"] = guarded(lambda: secondary_cfg5(args, ctx, rank, world, dist))
 
     if rank == 0:
         line = {
@@ -346,25 +439,9 @@ def run_ours(args):
         if e2e_u16 is not None:
             line["e2e_u16mm_depth"] = e2e_u16
         if router is not None:
-            if args.router == "p2p":
-                sent, dropped = router.stats()
-                line["routing"] = {"blocks_sent_rank0": int(sum(sent)), "records_dropped_rank0": int(dropped),
-                                   "bytes_sent_rank0": int(sum(sent)) * 4 * vol.RECORD_WORDS,
-                                   "route_ms_per_step_rank0": (float(np.mean([a.elapsed_time(b) for a, b in route_events]))
-                                                               if route_events else None),
-                                   "overlapped_with_fusion": bool(overlap),
-                                   "batch_order": ("last batch (frames that reach past the slab) first, routing on a side "
-                                                   "stream underneath the other batches, first batch last after the merge"
-                                                   if overlap else "ascending, routing after fusion"),
-                                   "transport": "export kernel stores 10 KiB block records straight into the owner's "
-                                                "memory over NVLink (CUDA IPC peer mapping); 4-byte NCCL all_reduce as "
-                                                "the export->merge fence; owner merges from its own HBM"}
-                assert dropped == 0, "receive region too small: raise --region-records"
-            else:
-                line["routing"] = {"blocks_sent_rank0": router.last_sent, "blocks_received_rank0": router.last_received,
-                                   "bytes_sent_rank0": router.last_sent * 4 * router.RECORD,
-                                   "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in route_events])),
-                                   "transport": "NCCL all_to_all_single (counts) + all_to_all_single (10 KiB block records)"}
+            line["routing"] = routing
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -443,9 +520,12 @@ def run_e2e(args, ctx, vol, depth_all, bgr_all, poses, world, dist, u16=False):
             "api": "TSDFVolume.integrate_views over pinned-host frames (H2D double-buffered) + counters() D2H"}
 
 
-def cpu_baseline(args, depth_all, bgr_all, poses):
+def cpu_baseline(args, depth_all, bgr_all, poses, gpu_counters=None, gpu_blocks=None):
+    """The oracle on the host cores over the same frames (copied from the GPU, so both sides see identical
+    inputs).  When it covers the whole step its counters must equal the GPU's: asserted, `parity_checked`."""
     from oracle import capi
-    n = args.cpu_frames
+    capi.set_num_threads(host_threads())
+    n = min(args.cpu_frames, args.frames)
     frames = [(depth_all[i].cpu().numpy(), bgr_all[i].cpu().numpy(), poses[i]) for i in range(n)]
     cores = capi.num_threads()
     ov = capi.TSDFVolume(VOXEL, TRUNC)
@@ -455,9 +535,19 @@ def cpu_baseline(args, depth_all, bgr_all, poses):
     for d, c, T in frames:
         ov.integrate(d, c, KINTR, T, 1.0, DEPTH_MAX)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"frames 0..{n - 1} of the workload's {args.frames} frames, one pass (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s wall",
-            "voxel_updates": ov.counters()["voxel_updates"]}
+    oc = ov.counters()
+    res = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"frames 0..{n - 1} of the workload's {args.frames} frames, one pass (touch + integrate), oracle/t3d_oracle.c with {cores} OpenMP threads, {dt:.1f} s wall",
+           "voxel_updates": oc["voxel_updates"], "block_frames": oc["block_frames"], "blocks": int(ov.num_blocks),
+           "parity_checked": False}
+    if gpu_counters is not None and n == args.frames:
+        # same inputs, same step: the integer outputs of the two arms must be identical
+        assert oc["voxel_updates"] == gpu_counters["voxel_updates"], (oc, gpu_counters)
+        assert oc["block_frames"] == gpu_counters["block_frames"], (oc, gpu_counters)
+        assert int(ov.num_blocks) == int(gpu_blocks), (ov.num_blocks, gpu_blocks)
+        res["parity_checked"] = True
+        res["parity"] = "voxel_updates, block_frames (block-frame pairs) and allocated blocks equal the GPU step's (asserted)"
+    return res
 
 
 # --------------------------------------------------------------------------- cfg3: ICP + TSDF
@@ -481,14 +571,11 @@ def cfg3_config(frames, args):
             "l2": "frames resident in HBM (14.5 MB each, >> L2 in total); model blocks re-read from HBM"}
 
 
-def run_cfg3(args):
-    """Secondary workload (not the driver's default line): the frame-to-model loop of cfg 3."""
+def measure_cfg3(args, ctx, F, steps, warmup, cpu_frames, stages=True):
+    """The frame-to-model loop of cfg 3 (ICP + TSDF) over F frames; returns the JSON-able result dict."""
     import torch
-    from textureless_3d_reconstruction_b200.runtime import get_context
     from textureless_3d_reconstruction_b200.tracking import FrameToModelTracker
-    ctx = get_context(0)
     dev = ctx.device
-    F = args.frames
     depth_all = torch.empty((F, H, W), dtype=torch.float32, device=dev)
     bgr_all = torch.empty((F, H, W, 3), dtype=torch.uint8, device=dev)
     poses = []
@@ -505,15 +592,15 @@ def run_cfg3(args):
         for i in range(F):
             trk.add_frame(depth_all[i], bgr_all[i], known_pose=poses[0] if i == 0 else None)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(ctx.device.index or 0)
     sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
@@ -524,15 +611,17 @@ def run_cfg3(args):
     its = [r.iterations for r in trk.icp_log if r is not None]
     fit = [r.fitness for r in trk.icp_log if r is not None]
     nblocks = trk.volume.num_blocks
-    # per-stage breakdown (synchronised host timers; one extra untimed pass)
-    trk.stage_ms = {}
-    step()
-    stages = {k: v / F for k, v in trk.stage_ms.items()}
-    trk.stage_ms = None
+    st = None
+    if stages:   # per-stage breakdown (synchronised host timers; one extra untimed pass)
+        trk.stage_ms = {}
+        step()
+        st = {k: v / F for k, v in trk.stage_ms.items()}
+        trk.stage_ms = None
     cpu = None
-    if not args.no_cpu:
-        from oracle import ref_tracker
-        n = min(args.cpu_frames3, F)
+    if not args.no_cpu and cpu_frames > 0:
+        from oracle import capi, ref_tracker
+        capi.set_num_threads(host_threads())
+        n = min(cpu_frames, F)
         ot = ref_tracker.FrameToModelTracker(KINTR, H, W, voxel_size=VOXEL, sdf_trunc=TRUNC, depth_max=DEPTH_MAX,
                                              icp_subsample=args.icp_subsample, icp_max_corr=args.icp_max_corr)
         hf = [(depth_all[i].cpu().numpy(), bgr_all[i].cpu().numpy()) for i in range(n)]
@@ -540,23 +629,190 @@ def run_cfg3(args):
         for i in range(n):
             ot.add_frame(hf[i][0], hf[i][1], known_pose=poses[0] if i == 0 else None)
         dt = time.perf_counter() - t0
-        from oracle import capi
+        # the GPU loop and its CPU restatement must agree on the poses of the frames both tracked
+        dpose = max(float(np.abs(np.asarray(trk.poses[i]) - np.asarray(ot.poses[i])).max()) for i in range(n))
         cpu = {"value": n / dt, "unit": UNIT, "cores": capi.num_threads(), "kind": "port",
                "sample": f"frames 0..{n - 1} (oracle/ref_tracker.py over oracle/t3d_oracle.c, OpenMP), {dt:.1f} s wall",
-               "pose_err_last_m": pose_error(ot.poses[-1], poses[n - 1])[0]}
-    line = {"metric": METRIC3, "value": F * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "pose_err_last_m": pose_error(ot.poses[-1], poses[n - 1])[0],
+               "max_abs_pose_difference_gpu_vs_cpu": dpose, "parity_checked": bool(dpose <= 1e-4)}
+        assert dpose <= 1e-4, f"tracked poses differ between the GPU loop and the CPU restatement: {dpose}"
+    line = {"metric": METRIC3, "value": F * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (TSDF) / f64 (ICP normal equations)",
             "data": "synthetic (tunnel T1, sigma=2 mm depth noise, seed 1234, generated on device)",
             "config": cfg3_config(F, args), "clocks": sampler.result(), "gpu_launches": int(launches),
-            "ms_per_frame": ms / args.steps / F, "stage_ms_per_frame_synchronised": stages,
+            "ms_per_frame": ms / steps / F, "stage_ms_per_frame_synchronised": st,
             "tracking": {"final_translation_error_m": errs[-1][0], "final_rotation_error_rad": errs[-1][1],
                          "max_translation_error_m": max(e[0] for e in errs), "trajectory_length_m": 0.25 * (F - 1),
                          "mean_icp_iterations": float(np.mean(its)) if its else None,
                          "mean_fitness": float(np.mean(fit)) if fit else None,
                          "last_target_points": trk.last_target[0]},
             "cpu_baseline": cpu, "blocks": int(nblocks)}
-    print(json.dumps(line), flush=True)
+    del trk, depth_all, bgr_all
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_cfg3(args):
+    """Secondary workload as its own line (`--workload cfg3`): the frame-to-model loop of cfg 3."""
+    from textureless_3d_reconstruction_b200.runtime import get_context
+    print(json.dumps(measure_cfg3(args, get_context(0), args.frames, args.steps, args.warmup, args.cpu_frames3)), flush=True)
+
+
+# --------------------------------------------------------------------------- secondary legs of the default line
+def guarded(fn):
+    """A secondary leg must never take the headline line down with it."""
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        return {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+
+
+def secondary_cfg3(args, ctx):
+    """BASELINE configs[2] in short: 120 frames of the ICP + TSDF loop (the metric's "(TSDF+ICP)")."""
+    r = measure_cfg3(args, ctx, 120, 1, 1, 4, stages=True)
+    keep = ("metric", "value", "unit", "ms_per_frame", "stage_ms_per_frame_synchronised", "tracking", "cpu_baseline",
+            "gpu_launches", "blocks")
+    out = {k: r[k] for k in keep}
+    out["workload"] = "BASELINE configs[2], first 120 of the 600 frames: frame-to-model point-to-plane ICP + TSDF fusion"
+    return out
+
+
+def secondary_cfg1(args, ctx):
+    """BASELINE configs[0]: the depth_to_reconstruction dense path on 30 synthetic 1080x1920 frames (scene S1):
+    back-project (subsample 2, the CLI default) -> voxel-downsample 5 mm -> statistical outlier removal -> host
+    arrays; the point count must equal the CPU path's."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import to_host
+    dev = ctx.device
+    n1, sub, vox = 30, 2, 0.005
+    d1 = torch.empty((n1, H, W), dtype=torch.float32, device=dev)
+    c1 = torch.empty((n1, H, W, 3), dtype=torch.uint8, device=dev)
+    p1 = []
+    for i in range(n1):
+        _, _, T = ctx.synth_frame(1, i, H, W, *KINTR, seed=SEED, depth=d1[i], bgr=c1[i])
+        p1.append((T[:, :3].copy(), T[:, 3:4].copy()))
+    fr1 = ctx.make_backproject_frames([d1[i] for i in range(n1)], [c1[i] for i in range(n1)], p1)
+
+    def run():
+        xyz, rgb, offs = ctx.backproject_batch(fr1, n1, H, W, fx=KINTR[0], fy=KINTR[1], cx=KINTR[2], cy=KINTR[3],
+                                               subsample=sub, min_depth=0.1, max_depth=50.0)
+        n = int(offs[-1].item())
+        ds = ctx.voxel_downsample(xyz[:n], rgb[:n], vox, sorted_output=True, want_idx=False)
+        pts, cols = ds["points"].contiguous(), ds["colors"].contiguous()
+        keep, _, _, _ = ctx.statistical_outlier(pts, 20, 2.0)
+        return n, to_host(ctx.compact_rows(pts, keep)), to_host(ctx.compact_rows(cols, keep))
+
+    run()
+    run()
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        n_in, ph, ch = run()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    out = {"workload": "BASELINE configs[0]: back-project + voxel-downsample-merge 30 synthetic 1080x1920 frames "
+                       "(subsample 2, voxel 5 mm, statistical outlier removal), frames resident in HBM -> host arrays",
+           "metric": "frames/s through depth_to_pointcloud + merge_pointclouds", "value": n1 / dt, "unit": UNIT,
+           "ms_per_step": dt * 1e3, "points_in": int(n_in), "points_out": int(len(ph)), "cpu_baseline": None}
+    if not args.no_cpu:
+        from oracle import capi
+        capi.set_num_threads(host_threads())
+        hd = [(d1[i].cpu().numpy(), c1[i].cpu().numpy()) for i in range(n1)]
+        t0 = time.perf_counter()
+        xs, cs = [], []
+        for i in range(n1):
+            x, c = capi.backproject(hd[i][0], hd[i][1], *KINTR, pose=p1[i], subsample=sub, min_depth=0.1, max_depth=50.0)
+            xs.append(x)
+            cs.append(c)
+        o = capi.voxel_downsample(np.concatenate(xs).astype(np.float64), np.concatenate(cs), vox)
+        keep, _, _ = capi.statistical_outlier(o["points"], 20, 2.0)
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n1 / dtc, "unit": UNIT, "cores": capi.num_threads(), "kind": "port",
+                               "sample": f"all 30 frames, oracle K1 (C, OpenMP) + R2 (serial hash, as Open3D) + R3 (OpenMP), {dtc:.1f} s wall",
+                               "points_out": int(keep.sum())}
+        assert int(keep.sum()) == len(ph), f"cfg1 point count differs: CPU {int(keep.sum())} vs GPU {len(ph)}"
+        out["cpu_baseline"]["parity_checked"] = True
+    del d1, c1
+    torch.cuda.empty_cache()
+    return out
+
+
+def secondary_cfg5(args, ctx, rank, world, dist):
+    """BASELINE configs[4] in short (N > 1 only): 64 frames per GPU at 2160x3840, 5 mm voxels, trunc 2 cm, blocks
+    routed to their z-slab owner after fusion; conservation asserted over all ranks."""
+    import torch
+    from textureless_3d_reconstruction_b200.distributed import CopyEngineBlockRouter, block_owner_range
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H5, W5, K5, V5, T5 = 3840, 2160, (3438.0, 3438.0, 1080.0, 1920.0), 0.005, 0.02
+    F5, B5, steps = 64, 64, 2
+    dev = ctx.device
+    depth = torch.empty((F5, H5, W5), dtype=torch.float32, device=dev)
+    bgr = torch.empty((F5, H5, W5, 3), dtype=torch.uint8, device=dev)
+    poses = []
+    for i in range(F5):
+        _, _, T = ctx.synth_frame(0, rank * F5 + i, H5, W5, *K5, seed=SEED, noise_sigma=NOISE, depth=depth[i], bgr=bgr[i])
+        poses.append(T)
+    vol = TSDFVolume(V5, T5, block_capacity=1_500_000, ctx=ctx)
+    views = vol.make_frame_views([depth[i] for i in range(F5)], [bgr[i] for i in range(F5)], [K5] * F5, poses)
+    router = CopyEngineBlockRouter(vol, rank, world, slab_frames=F5, frame_advance=0.25, block_size=V5 * 8,
+                                   region_records=262144)
+
+    def step():
+        vol.reset()
+        vol.integrate_sequence(views, F5, H5, W5, B5, False, 1.0, DEPTH_MAX)
+        router.route()
+
+    step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    router.route_events.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    cnt = vol.counters()
+    sent, _ = router.stats()
+    lo, hi = block_owner_range(rank, world, router.slab_blocks)
+    _, _, w_owned, _ = vol.export_blocks_range(2, max(lo, -(1 << 20)), min(hi, 1 << 20))
+    t = torch.tensor([ms, float(w_owned.double().sum().item()), float(cnt["voxel_updates"])], dtype=torch.float64, device=dev)
+    del w_owned
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t)
+    assert int(t[1].item()) == int(t[2].item()), f"cfg5 routing lost or duplicated weight: {t[1].item()} != {t[2].item()}"
+    ms = float(tmax[0].item())
+    out = {"workload": f"BASELINE configs[4] in short: {F5} synthetic 2160x3840 frames per GPU, 5 mm voxels, trunc 2 cm, "
+                       f"blocks routed to their z-slab owner (copy-engine router), {world} GPUs",
+           "metric": "RGB-D frames fused/sec @2160x3840 (TSDF integration + block routing, cfg5)",
+           "value": F5 * world * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "blocks_rank0": int(vol.num_blocks), "routed_blocks_rank0": int(sum(sent)),
+           "routed_bytes_rank0": int(sum(sent)) * 4 * vol.RECORD_WORDS,
+           "route_ms_per_step_rank0": float(np.mean([a.elapsed_time(b) for a, b in router.route_events])),
+           "conservation": {"sum_owned_weights_all_ranks": int(t[1].item()), "sum_voxel_updates_all_ranks": int(t[2].item()),
+                            "checked": True},
+           "cpu_baseline": None}
+    if rank == 0 and not args.no_cpu:
+        from oracle import capi
+        capi.set_num_threads(host_threads())
+        ov = capi.TSDFVolume(V5, T5)
+        hf = [(depth[i].cpu().numpy(), bgr[i].cpu().numpy()) for i in range(2)]
+        t0 = time.perf_counter()
+        for i in range(2):
+            ov.integrate(hf[i][0], hf[i][1], K5, poses[i], 1.0, DEPTH_MAX)
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2 / dtc, "unit": UNIT, "cores": capi.num_threads(), "kind": "port",
+                               "sample": f"frames 0..1 of rank 0 (touch + integrate), oracle/t3d_oracle.c, {dtc:.1f} s wall"}
+    router.close()
+    del depth, bgr, vol
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -570,13 +826,19 @@ def main():
     ap.add_argument("--block-capacity", type=int, default=600_000)
     ap.add_argument("--cpu-frames", type=int, default=300,
                     help="frames of the workload the CPU legs fuse per pass (300 = the whole cfg2 job, ~4 s on 16 cores)")
+    ap.add_argument("--ref-frames", type=int, default=100,
+                    help="--impl reference: frames of the workload fused per step (bounded sample: 100 frames keep the whole "
+                         "run, host-side frame generation included, within a few minutes)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="(tuning) skip the host-buffer leg")
     ap.add_argument("--serial-batches", action="store_true", help="(tuning) no K4/K5 overlap")
     ap.add_argument("--no-overlap", action="store_true",
                     help="(N > 1, p2p router) route after fusion instead of underneath it")
-    ap.add_argument("--router", choices=["p2p", "nccl"], default="p2p",
-                    help="N>1 block routing: peer-memory stores over NVLink (default) or NCCL all_to_all")
+    ap.add_argument("--router", choices=["ce", "p2p", "nccl"], default="ce",
+                    help="N>1 block routing: copy-engine peer copies (default), peer-memory stores from an export "
+                         "kernel, or NCCL all_to_all")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the short cfg3 / cfg1 (N=1) and cfg5 (N>1) runs reported under `secondary`")
     ap.add_argument("--region-records", type=int, default=16384,
                     help="p2p router: receive capacity per source rank, in 10 KiB block records")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg5"], default="cfg2",
@@ -601,6 +863,8 @@ def main():
             args.block_capacity = 1_500_000
         if args.cpu_frames == 300:
             args.cpu_frames = 8
+        if args.ref_frames == 100:
+            args.ref_frames = 8
         if args.region_records == 16384:
             args.region_records = 65536       # 4x more blocks per metre of look-ahead than cfg2
     if args.impl == "reference":

@@ -16,7 +16,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        # what a gather-bound kernel is bound BY: L1 wavefronts / sector lookups, L2 sector lookups, L2->L1 bytes
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum",
+        "l1tex__t_sectors.sum", "l1tex__t_sectors_lookup_miss.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "lts__t_sectors.sum", "lts__t_sectors.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path):
@@ -47,8 +54,10 @@ def full(path):
     for r in rows[2:]:
         print("kernel:", r[h.index("Kernel Name")][:140])
         for k in KEYS:
-            if k in h:
-                print(f"  {k:68s} {r[h.index(k)]:>16s} {units[h.index(k)]}")
+            cols = [i for i, name in enumerate(h) if name == k or name.endswith("." + k)]   # some live under a section prefix
+            cols = [i for i in cols if r[i] != ""]
+            if cols:
+                print(f"  {k:68s} {r[cols[0]]:>16s} {units[cols[0]]}")
         st = [(float(r[i] or 0), h[i]) for i in range(len(h)) if "pcsamp_warps_issue_stalled" in h[i] and not h[i].endswith("_not_issued")]
         tot = sum(v for v, _ in st) or 1.0
         for v, c in sorted(st, reverse=True)[:7]:
@@ -56,8 +65,14 @@ def full(path):
 
 
 def traffic(path, kernel="integrate_kernel"):
-    """JSON for bench.py's roofline.traffic: mean dram read+write bytes per launch of `kernel`."""
+    """JSON for bench.py's roofline.traffic: mean dram read+write bytes per launch of `kernel`, tagged with the
+    sha256 of csrc/tsdf.cu as it is NOW (run this right after the capture): bench.py refuses to replay the
+    number once the kernel source has changed."""
+    import hashlib
     import json
+    import pathlib
+    src = pathlib.Path(__file__).resolve().parent.parent / "textureless_3d_reconstruction_b200" / "csrc" / "tsdf.cu"
+    sha = hashlib.sha256(src.read_bytes()).hexdigest()
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h, units = rows[0], rows[1]
@@ -71,7 +86,7 @@ def traffic(path, kernel="integrate_kernel"):
         us = float(r[h.index("gpu__time_duration.sum")])
         per.append({"read": rd, "write": wr, "duration_" + units[h.index("gpu__time_duration.sum")]: us})
     n = max(len(per), 1)
-    print(json.dumps({"kernel": kernel, "launches": len(per),
+    print(json.dumps({"kernel": kernel, "launches": len(per), "kernel_source_sha256": sha,
                       "dram_bytes_per_launch": sum(p["read"] + p["write"] for p in per) / n,
                       "dram_read_per_launch": sum(p["read"] for p in per) / n,
                       "dram_write_per_launch": sum(p["write"] for p in per) / n,
