@@ -202,7 +202,7 @@ __global__ void hg_count_kernel(const float* __restrict__ tgt, const __grid_cons
 
 // cells get their [start, start+count) range from a running cursor: cell order is
 // irrelevant, only contiguity inside a cell matters
-__global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
+__global__ void hg_alloc_kernel(const __grid_constant__ HGrid g, int with_coarse) {
   // the loop bound is warp-uniform (the table size is a multiple of 32 and so is the stride), so the
   // cursor can be advanced once per warp: tens of thousands of returning atomics on one address
   // would otherwise serialise in L2
@@ -223,6 +223,7 @@ __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g) {
     base = __shfl_sync(0xffffffffu, base, 31);
     if (!c) continue;
     g.start[s] = base + (incl - c);
+    if (!with_coarse) continue;
     // note this fine cell's coarse cell (2h); hg_dilate_kernel then marks the 27 coarse cells around
     // every occupied coarse cell — one dilation per coarse cell instead of one per fine cell
     int fx, fy, fz;
@@ -424,8 +425,12 @@ constexpr int NN_GROUP = 8;  // lanes per query
 __global__ void __launch_bounds__(NN_THREADS, 4)
     icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
                   const long long* n_src_dev, double r2, const IcpState* st, int* __restrict__ corr,
-                  double* __restrict__ corr_d2) {
+                  double* __restrict__ corr_d2, int near_filter) {
   if (*reinterpret_cast<const volatile int*>(&st->done)) return;
+  // from the second linearisation on, corr[] holds the previous round's answer for this registration: it
+  // seeds the search as the incumbent (exact: any valid candidate may), and because the pose moves little
+  // between rounds the seed is almost always the answer already, so nearly every cell fails the box test
+  const bool warm = *reinterpret_cast<const volatile int*>(&st->round) > 0;
   if (n_src_dev) { const long long v = *n_src_dev; n_src = v < n_src ? v : n_src; }
   __shared__ double s_T[12];
   if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
@@ -445,14 +450,23 @@ __global__ void __launch_bounds__(NN_THREADS, 4)
     const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
     NNState nn;
     nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
+    if (warm) {
+      const int pj = corr[i];
+      if (pj >= 0) {
+        const float4 t = __ldg(g.xyzi + pj);
+        const double ddx = (double)t.x - sx, ddy = (double)t.y - sy, ddz = (double)t.z - sz;
+        const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+        if (d2 <= r2) { nn.best = d2; nn.bj = pj; nn.bo = __float_as_uint(t.w); }
+      }
+    }
     int cx, cy, cz;
-    if (hg_cell(g, sx, sy, sz, cx, cy, cz) && hg_near_target(g, cx, cy, cz)) {  // group-uniform
+    if (hg_cell(g, sx, sy, sz, cx, cy, cz) && (!near_filter || hg_near_target(g, cx, cy, cz))) {  // group-uniform
       const double lx = sx - (double)cx * g.h, ly = sy - (double)cy * g.h, lz = sz - (double)cz * g.h;
       const double hh = 0.5 * g.h;
       const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
       {  // step 1: one octant cell per lane
         const int dx = (sub & 1) ? ox : 0, dy = (sub & 2) ? oy : 0, dz = (sub & 4) ? oz : 0;
-        if (sub == 0 || hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) <= nn.best)
+        if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) <= nn.best)  // (0 for the query's own cell)
           hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
       }
       nn_group_min(nn, gmask);
@@ -656,7 +670,11 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   g.n = n_tgt;
   g.n_dev = n_tgt_dev;
   const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
-  const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * 4 ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * 4);
+  // one CTA per SM: the work per round is tiny (one gather + 27 FMAs per point), what costs is the 29-double
+  // reduction tree per warp and the last CTA's pass over the per-CTA partials — both shrink with the grid
+  static int acc_mult = -1;
+  if (acc_mult < 0) { const char* e = getenv("T3D_ICP_ACC_MULT"); acc_mult = e ? atoi(e) : 1; if (acc_mult < 1) acc_mult = 1; }
+  const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * acc_mult ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * acc_mult);
   const long long want_nn = (n_src * NN_GROUP + NN_THREADS - 1) / NN_THREADS;
   const int grid_nn = (int)(want_nn < (long long)ctx->num_sms * 8 ? (want_nn > 0 ? want_nn : 1) : (long long)ctx->num_sms * 8);
   if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid_acc * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
@@ -678,21 +696,26 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   const int hgrid = (int)((hc + 255) / 256 < 2368 ? (hc + 255) / 256 : 2368);
 
   // grid build + initial state + `rounds` linearisations + result read-back, all on stream st
+  // The dilated coarse occupancy set answers "no target within reach" with one probe; it pays when many
+  // queries are far from the target (a bad initial guess, partial overlap).  Frame-to-model tracking
+  // (device-count mode) registers a frame against the surface it was predicted from: nearly every query has
+  // a target nearby, so the set's construction (a table scan + 27 inserts per coarse cell) is skipped.
+  const int near_filter = n_src_dev == nullptr ? 1 : 0;
   auto enqueue_all = [&](int rounds, bool with_build) -> int {
     if (with_build) {
       T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
       T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
-      T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
+      if (near_filter) T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
       T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
       hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
-      hg_alloc_kernel<<<hgrid, 256, 0, st>>>(g);
-      hg_dilate_kernel<<<hgrid, 256, 0, st>>>(g);
+      hg_alloc_kernel<<<hgrid, 256, 0, st>>>(g, near_filter);
+      if (near_filter) hg_dilate_kernel<<<hgrid, 256, 0, st>>>(g);
       hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
       T3D_LAUNCH_CHECK();
       T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
     }
     for (int r = 0; r < rounds; ++r) {
-      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2);
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
       icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, min_points, max_iter,
                                                         rel_fitness, rel_rmse, dst, corr, corr_d2, partial);
     }
