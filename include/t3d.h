@@ -210,6 +210,10 @@ typedef struct t3d_frame_view {
   const uint8_t* bgr;    /* H*W*3 u8 BGR (nullable: no colour integration)     */
   float K[4];            /* fx, fy, cx, cy                                     */
   float T_cw[12];        /* world->camera extrinsic, row-major 3x4 [R|t]       */
+  const uint8_t* conf_mask; /* H*W u8, nullable (north_star "confidence masking"; the reference has no
+                          * confidence map): a pixel whose byte is 0 carries no measurement —
+                          * K4 casts no ray through it and K5 updates no voxel from it, exactly as if its
+                          * depth were 0.  Same convention as t3d_backproject's conf_mask.              */
 } t3d_frame_view;
 
 int t3d_tsdf_create(t3d_ctx* ctx, const t3d_tsdf_params* p, t3d_tsdf** out);

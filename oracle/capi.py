@@ -199,17 +199,29 @@ class TSDFVolume:
             return np.ascontiguousarray(depth), 1
         return np.ascontiguousarray(depth, np.float32), 0
 
-    def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0):
+    @staticmethod
+    def _conf(conf, shape):
+        if conf is None:
+            lib().o_tsdf_set_conf(None)
+            return None
+        conf = np.ascontiguousarray(conf, np.uint8)
+        assert conf.shape == shape
+        lib().o_tsdf_set_conf(_p(conf))
+        return conf
+
+    def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0, conf_mask=None):
         depth, u16 = self._depth(depth)
+        conf_mask = self._conf(conf_mask, depth.shape)
         H, W = depth.shape
         K = np.ascontiguousarray(K, np.float32)
         T = np.ascontiguousarray(np.asarray(T_cw, np.float32)[:3, :4])
         out = np.empty(((H // 4) * (W // 4) * 4 + 1, 3), np.int32)
         n = lib().o_tsdf_touch(self._h, _p(depth), C.c_int(u16), C.c_int(H), C.c_int(W), _p(K), _p(T),
                                C.c_float(depth_scale), C.c_float(depth_max), _p(out))
+        lib().o_tsdf_set_conf(None)
         return out[:n].copy()
 
-    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0, keys=None, literal=False):
+    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0, keys=None, literal=False, conf_mask=None):
         """R4 + R5 for one frame.  literal=True: R5 exactly as SURVEY 8c writes it (true divisions, no FMA,
         no reciprocals; o_tsdf_integrate_literal) instead of the kernel-ordered arithmetic."""
         depth, u16 = self._depth(depth)
@@ -218,11 +230,13 @@ class TSDFVolume:
         K = np.ascontiguousarray(K, np.float32)
         T = np.ascontiguousarray(np.asarray(T_cw, np.float32)[:3, :4])
         if keys is None:
-            keys = self.touch(depth, K, T, depth_scale, depth_max)
+            keys = self.touch(depth, K, T, depth_scale, depth_max, conf_mask=conf_mask)
         keys = np.ascontiguousarray(keys, np.int32)
+        conf_mask = self._conf(conf_mask, depth.shape)
         fn = lib().o_tsdf_integrate_literal if literal else lib().o_tsdf_integrate
         fn(self._h, _p(depth), C.c_int(u16), _p(bgr), C.c_int(H), C.c_int(W), _p(K), _p(T),
            C.c_float(depth_scale), C.c_float(depth_max), _p(keys), C.c_int64(len(keys)))
+        lib().o_tsdf_set_conf(None)
         return keys
 
     def export_flags(self):

@@ -3,11 +3,11 @@
 # Each ncu pass runs only after the identical plain command exited 0.
 #   usage: bash profiles/capture.sh <tag>        e.g. r1
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 # 1) launch list of the default bench command (device-resident leg only; shares, not absolutes)
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-secondary"
 $CMD > $OUT/plain_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"touch|integrate" -c 200 --csv \
     --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1

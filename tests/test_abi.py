@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from textureless_3d_reconstruction_b200 import _lib
     assert ctypes.sizeof(_lib.BackprojectParams) == 8 * 4 + 7 * 8 + 12 * 8
     assert ctypes.sizeof(_lib.TsdfParams) == 32
-    assert ctypes.sizeof(_lib.FrameView) == 16 + 16 + 48
+    assert ctypes.sizeof(_lib.FrameView) == 16 + 16 + 48 + 8        # depth, bgr | K | T_cw | conf_mask
     assert ctypes.sizeof(_lib.IcpResult) == 16 * 8 + 16 + 8 + 8
 
 

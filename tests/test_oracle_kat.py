@@ -184,3 +184,23 @@ def test_r8_known_answer(oracle):
     JtJ = np.outer(J, J)[np.triu_indices(6)]
     assert np.allclose(one[:21], JtJ) and np.allclose(one[21:27], J * np.float32(3.0 - np.float32(2.9)), atol=1e-7)
     assert one[28] == 1.0 and np.isclose(one[27], 0.01, atol=1e-6)
+
+
+def test_tsdf_confidence_mask_equals_zeroed_depth(oracle):
+    """Confidence masking (north_star; no reference code): masked pixels behave exactly like pixels without depth."""
+    from textureless_3d_reconstruction_b200 import synthetic as S
+    H, W = 120, 68
+    it = S.scaled_intrinsics(H, W)
+    K = (it["fx"], it["fy"], it["cx"], it["cy"])
+    rng = np.random.default_rng(3)
+    a, b = oracle.TSDFVolume(0.02, 0.08), oracle.TSDFVolume(0.02, 0.08)
+    for i in range(3):
+        d, c, T = S.synth_frame(0, i, H, W, *K, noise_sigma=0.002)
+        m = (rng.random((H, W)) > 0.4).astype(np.uint8)
+        a.integrate(d, c, K, T, 1.0, 5.0, conf_mask=m)
+        dz = d.copy()
+        dz[m == 0] = 0
+        b.integrate(dz, c, K, T, 1.0, 5.0)
+    assert a.counters() == b.counters() and a.counters()["voxel_updates"] > 1000
+    for x, y in zip(a.export(), b.export()):
+        assert np.array_equal(x, y)

@@ -350,3 +350,54 @@ def test_full_size_tracking_properties(ctx):
         a.add_frame(d, c, known_pose=T)
         b.integrate(d, c, K, T, 1.0, 5.0)
     assert a.volume.counters() == b.counters() and a.volume.num_blocks == b.num_blocks
+
+
+def test_confidence_mask(ctx, oracle):
+    """north_star "confidence masking" in TSDF fusion (t3d_frame_view.conf_mask): a pixel whose mask byte is 0
+    carries no measurement.  (i) GPU == oracle with the same mask, bit for bit; (ii) independent of any oracle:
+    fusing with a mask == fusing the same frames with the depth of the masked pixels set to 0."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume
+    H, W = 240, 136
+    fr, K = frames(4, H, W)
+    rng = np.random.default_rng(7)
+    masks = []
+    for i in range(4):
+        m = (rng.random((H, W)) > 0.3).astype(np.uint8) * rng.integers(1, 256, (H, W)).astype(np.uint8)
+        m[40:90, 20:70] = 0                                   # a solid masked rectangle as well as salt-and-pepper
+        masks.append(m)
+    a = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)     # masked
+    b = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)     # depth zeroed instead
+    full = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)  # no mask
+    ov = oracle.TSDFVolume(0.01, 0.04)
+    for (d, c, T), m in zip(fr, masks):
+        dd, cc, mm = torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(m).cuda()
+        gk = a.touch(dd, K, T, 1.0, 5.0, conf_mask=mm).cpu().numpy()
+        ok = ov.touch(d, K, T, 1.0, 5.0, conf_mask=m)
+        assert key_rows(gk) == key_rows(ok) and len(gk) == len(ok)
+        a.integrate(dd, cc, K, T, 1.0, 5.0, conf_mask=mm)
+        ov.integrate(d, c, K, T, 1.0, 5.0, conf_mask=m)
+        dz = d.copy()
+        dz[m == 0] = 0.0
+        b.integrate(torch.from_numpy(dz).cuda(), cc, K, T, 1.0, 5.0)
+        full.integrate(dd, cc, K, T, 1.0, 5.0)
+    assert a.counters() == ov.counters() == b.counters()
+    assert a.counters()["voxel_updates"] < 0.8 * full.counters()["voxel_updates"]
+    ea = by_key(*[x.cpu().numpy() for x in a.export_blocks()])
+    eb = by_key(*[x.cpu().numpy() for x in b.export_blocks()])
+    eo = by_key(*ov.export())
+    for x, y, z in zip(ea, eb, eo):
+        bits = (lambda q: q.view(np.uint32)) if x.dtype == np.float32 else (lambda q: q)
+        assert np.array_equal(bits(x), bits(y)) and np.array_equal(bits(x), bits(z))
+    # a batch with a mask on some frames only
+    c2 = TSDFVolume(0.01, 0.04, block_capacity=60000, ctx=ctx)
+    ds = [torch.from_numpy(f[0]).cuda() for f in fr]
+    cs = [torch.from_numpy(f[1]).cuda() for f in fr]
+    views = c2.make_frame_views(ds, cs, [K] * 4, [f[2] for f in fr], [torch.from_numpy(m).cuda() for m in masks])
+    c2.integrate_sequence(views, 4, H, W, batch=4, depth_scale=1.0, depth_max=5.0)
+    ec = by_key(*[x.cpu().numpy() for x in c2.export_blocks()])
+    for x, y in zip(ea, ec):
+        bits = (lambda q: q.view(np.uint32)) if x.dtype == np.float32 else (lambda q: q)
+        assert np.array_equal(bits(x), bits(y))
+    with pytest.raises(ValueError):
+        a.integrate(ds[0], cs[0], K, fr[0][2], 1.0, 5.0, conf_mask=torch.zeros((H, W + 1), dtype=torch.uint8, device="cuda"))

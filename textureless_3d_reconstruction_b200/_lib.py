@@ -48,6 +48,7 @@ class TsdfParams(C.Structure):
 class FrameView(C.Structure):
     _fields_ = [
         ("depth", C.c_void_p), ("bgr", C.c_void_p), ("K", C.c_float * 4), ("T_cw", C.c_float * 12),
+        ("conf_mask", C.c_void_p),
     ]
 
 

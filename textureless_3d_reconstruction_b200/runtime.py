@@ -542,12 +542,15 @@ class TSDFVolume:
         check(self.lib.t3d_tsdf_reset(self.handle, _stream()))
 
     @staticmethod
-    def make_frame_views(depths, bgrs, Ks, T_cws):
-        """Build the host-side frame descriptor array once (bench: outside the timed loop)."""
+    def make_frame_views(depths, bgrs, Ks, T_cws, conf_masks=None):
+        """Build the host-side frame descriptor array once (bench: outside the timed loop).
+        conf_masks: optional per-frame (H, W) uint8 CUDA tensors (0 = pixel carries no measurement)."""
         n = len(depths)
         arr = (FrameView * n)()
         for i in range(n):
-            _check_frame(depths[i], bgrs[i] if bgrs is not None else None, None, f"TSDF frame {i}")
+            cm = conf_masks[i] if conf_masks is not None else None
+            _check_frame(depths[i], bgrs[i] if bgrs is not None else None, cm, f"TSDF frame {i}")
+            arr[i].conf_mask = cm.data_ptr() if cm is not None else None
             if depths[i].shape != depths[0].shape or depths[i].dtype != depths[0].dtype:
                 raise ValueError("TSDF integration: every frame of a batch must have the same size and dtype")
             arr[i].depth = depths[i].data_ptr()
@@ -594,12 +597,12 @@ class TSDFVolume:
         if err:
             raise err[0]
 
-    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0):
+    def integrate(self, depth, bgr, K, T_cw, depth_scale=1.0, depth_max=5.0, conf_mask=None):
         """Fuse one frame.  depth: (H,W) f32|u16 CUDA tensor; bgr: (H,W,3) u8 or None;
-        K=(fx,fy,cx,cy); T_cw: world->camera 4x4 or 3x4."""
+        K=(fx,fy,cx,cy); T_cw: world->camera 4x4 or 3x4; conf_mask: optional (H,W) u8, 0 = masked pixel."""
         torch = _torch()
         H, W = depth.shape
-        views = self.make_frame_views([depth], [bgr], [K], [T_cw])
+        views = self.make_frame_views([depth], [bgr], [K], [T_cw], None if conf_mask is None else [conf_mask])
         self.integrate_views(views, 0, 1, H, W, depth.dtype in (torch.uint16, torch.int16), depth_scale, depth_max)
 
     def integrate_batch(self, depths, bgrs, K, T_cws, depth_scale=1.0, depth_max=5.0):
@@ -610,11 +613,11 @@ class TSDFVolume:
         self.integrate_sequence(views, n, H, W, self.MAX_BATCH, depths[0].dtype in (torch.uint16, torch.int16),
                                 depth_scale, depth_max)
 
-    def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0):
+    def touch(self, depth, K, T_cw, depth_scale=1.0, depth_max=5.0, conf_mask=None):
         """K4 only: unique block keys (int32 [n,3], device) touched by one frame."""
         torch = _torch()
         H, W = depth.shape
-        views = self.make_frame_views([depth], None, [K], [T_cw])
+        views = self.make_frame_views([depth], None, [K], [T_cw], None if conf_mask is None else [conf_mask])
         cap = (H // 4) * (W // 4) * 4 + 1
         keys = torch.empty((cap, 3), dtype=torch.int32, device=depth.device)
         n = torch.zeros(1, dtype=torch.int64, device=depth.device)
