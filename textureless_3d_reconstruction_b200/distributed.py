@@ -381,7 +381,8 @@ class CopyEngineBlockRouter(P2PBlockRouter):
         if nb < 3 or batch < reach:
             raise ValueError(f"overlapped routing needs >= 3 batches of >= {reach} frames (got {nb} x {batch})")
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.ctx.device)
+            # high priority: at a K5 launch boundary the routing kernels are scheduled before the next K5's CTAs
+            self._side = torch.cuda.Stream(device=self.ctx.device, priority=-1)
             self._done = C.c_void_p()
             _lib.check(self.lib.t3d_event_create(C.byref(self._done)))
             self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
