@@ -244,14 +244,17 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
  * into the last batch):
  *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch 0 — every
  *     block batch 0 touches exists and no allocation is in flight at that point;
- *   after_batch0(user, touch_event, event): called ON THE HOST, inside this call, right after K5 of
- *     batch 0 was enqueued; `touch_event` (a cudaEvent_t) completes with K4 of batch 0 (from then on
- *     nblocks_after_touch0 and the keys of those blocks are final), `event` with K5 of batch 0.  The
- *     callee enqueues its own work on another stream (t3d_stream_wait_event) and records its
- *     completion event;
- *   wait_before_last (cudaEvent_t, nullable): K4 and K5 of the last batch wait for it.
+ *   after_batch0(user, phase, event_a, event_b): called ON THE HOST, inside this call, twice:
+ *     phase 0, right after K5 of batch 0 was enqueued: event_a (a cudaEvent_t) completes with K4 of batch 0
+ *       (from then on nblocks_after_touch0 and the keys of those blocks are final), event_b with K5 of
+ *       batch 0.  The callee enqueues its own work on another stream (t3d_stream_wait_event);
+ *     phase 1, right after K4 of the LAST batch was enqueued: event_a completes with it (event_b is NULL).
+ *       The callee enqueues what must run between K4 and K5 of the last batch (the merge of incoming
+ *       blocks: it allocates blocks like K4 does, so it is ordered after it) and records its completion
+ *       event, wait_before_last, before returning;
+ *   wait_before_last (cudaEvent_t, nullable): K5 of the last batch waits for it (without a hook: K4 too).
  * Needs at least 2 batches when any hook is given. */
-typedef void (*t3d_sequence_hook)(void* user, void* event_after_touch0, void* event_after_batch0);
+typedef void (*t3d_sequence_hook)(void* user, int phase, void* event_a, void* event_b);
 int t3d_tsdf_integrate_sequence_hooked(t3d_tsdf* v, const t3d_frame_view* frames_h,
                                        int n_frames, int batch, int H, int W,
                                        int depth_is_u16, float depth_scale, float depth_max,

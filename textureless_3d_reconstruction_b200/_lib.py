@@ -63,7 +63,7 @@ _lib = None
 
 # name -> (restype, argtypes)
 _VP, _I, _I64, _D, _F = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
-SEQUENCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)  # t3d_sequence_hook(user, touch_event, event)
+SEQUENCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)  # t3d_sequence_hook(user, phase, event_a, event_b)
 
 _SIGS = {
     "t3d_last_error": (C.c_char_p, []),

@@ -190,19 +190,23 @@ class P2PBlockRouter:
                 self._regions[parity][d] = self.peers[parity][d] + self.HEADER + rank * self.region_bytes
                 self._counts[parity][d] = self.peers[parity][d] + 4 * rank
 
-    def route(self, n_blocks_dev=None):
-        import ctypes as C
+    def _export(self, n_blocks_dev=None):
+        """export kernel (peer stores) + fence, on the current stream; returns the receive-buffer parity."""
         import torch.distributed as dist
         from . import _lib
         from .runtime import _ptr, _stream
-        if self.world == 1:
-            return
         par = self.step & 1
         self.step += 1
         _lib.check(self.lib.t3d_tsdf_route_export_p2p(self.vol.handle, self.AXIS, self.slab_blocks, self.world, self.rank,
                                                       self._regions[par], self._counts[par], self.region_records,
                                                       _ptr(self.fill), _ptr(n_blocks_dev), _stream()))
         dist.all_reduce(self.token, group=self.group)     # every rank's export precedes every rank's merge
+        return par
+
+    def _merge(self, par):
+        import ctypes as C
+        from . import _lib
+        from .runtime import _stream
         base = self.local[par]
         for s in range(self.world):
             if s != self.rank:
@@ -210,6 +214,11 @@ class P2PBlockRouter:
                     self.vol.handle, C.c_void_p(base + self.HEADER + s * self.region_bytes), C.c_void_p(base + 4 * s),
                     self.region_records, _stream()))
         _lib.check(self.lib.t3d_memset_async(C.c_void_p(base), 0, self.HEADER, _stream()))
+
+    def route(self, n_blocks_dev=None):
+        if self.world == 1:
+            return
+        self._merge(self._export(n_blocks_dev))
 
     # ---- routing that overlaps fusion -------------------------------------------------------------
     # The frames whose blocks must travel (the last ceil(depth_max / frame_advance) + 2 of a rank's
@@ -246,12 +255,18 @@ class P2PBlockRouter:
             self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
         side = self._side
 
-        def after_batch0(_ev_touch, ev):
+        state = {}
+
+        def after_batch0(phase, ev_a, ev_b):
             h = C.c_void_p(side.cuda_stream)
-            _lib.check(self.lib.t3d_stream_wait_event(h, ev))
             with torch.cuda.stream(side):
-                self.route(n_blocks_dev=self._snap)
-            _lib.check(self.lib.t3d_event_record(self._done, h))
+                if phase == 0:      # behind K5 of batch 0: export + fence, underneath the middle batches
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
+                    state["par"] = self._export(self._snap)
+                else:               # behind K4 of the last batch (both allocate blocks): merge, then K5 of the last batch
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
+                    self._merge(state["par"])
+                    _lib.check(self.lib.t3d_event_record(self._done, h))
 
         self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, after_batch0,
                                            self._done, depth_is_u16, depth_scale, depth_max)
@@ -325,7 +340,7 @@ class CopyEngineBlockRouter(P2PBlockRouter):
         return counts
 
     def _send(self, counts, n_blocks_dev):
-        """pack -> per-destination peer copies -> fence -> merge, all on the current stream."""
+        """pack -> per-destination peer copies -> fence, all on the current stream; returns the buffer parity."""
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -355,11 +370,17 @@ class CopyEngineBlockRouter(P2PBlockRouter):
                 _lib.check(self.lib.t3d_memcpy_async(self._counts[par][d], C.c_void_p(self.counts_dev.data_ptr() + 4 * d),
                                                      4, _stream()))
         dist.all_reduce(self.token, group=self.group)     # every rank's copies precede every rank's merge
+        self.last_counts = counts
+        return par
+
+    def _merge_all(self, par):
+        """ONE fused insert + merge launch pair for every source's region, then the header is cleared."""
+        from . import _lib
+        from .runtime import _stream
         local = self.local[par]
         _lib.check(self.lib.t3d_tsdf_merge_records_multi(self.vol.handle, C.c_void_p(local), self.HEADER, self.region_bytes,
                                                          self.world, self.rank, self.region_records, _stream()))
         _lib.check(self.lib.t3d_memset_async(C.c_void_p(local), 0, self.HEADER, _stream()))
-        self.last_counts = counts
 
     def route(self, n_blocks_dev=None):
         import torch
@@ -367,7 +388,7 @@ class CopyEngineBlockRouter(P2PBlockRouter):
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        self._send(self._read_counts(n_blocks_dev), n_blocks_dev)
+        self._merge_all(self._send(self._read_counts(n_blocks_dev), n_blocks_dev))
         e1.record()
         self.route_events.append((e0, e1))
 
@@ -388,21 +409,31 @@ class CopyEngineBlockRouter(P2PBlockRouter):
             self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
         side = self._side
 
-        def after_batch0(ev_touch, ev):
+        state = {}
+
+        def after_batch0(phase, ev_a, ev_b):
             h = C.c_void_p(side.cuda_stream)
             with torch.cuda.stream(side):
-                # the blocks that will travel exist once K4 of batch 0 is done: count them (host read) while
-                # K5 of batch 0 is still running ...
-                _lib.check(self.lib.t3d_stream_wait_event(h, ev_touch))
-                counts = self._read_counts(self._snap)
-                # ... and pack / copy / merge behind K5 of batch 0, underneath the fusion of the middle batches
-                _lib.check(self.lib.t3d_stream_wait_event(h, ev))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                self._send(counts, self._snap)
-                e1.record()
-                self.route_events.append((e0, e1))
-            _lib.check(self.lib.t3d_event_record(self._done, h))
+                if phase == 0:
+                    # the blocks that will travel exist once K4 of batch 0 is done: count them (host read) while
+                    # K5 of batch 0 is still running ...
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
+                    counts = self._read_counts(self._snap)
+                    # ... and pack / copy / fence behind K5 of batch 0, underneath the fusion of the middle batches
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
+                    state["e0"] = torch.cuda.Event(enable_timing=True)
+                    state["e0"].record()
+                    state["par"] = self._send(counts, self._snap)
+                else:
+                    # K4 of the last batch has been enqueued (it runs ahead, hidden under K5 of the batch before);
+                    # the merge allocates blocks like K4 does, so it follows it — and K5 of the last batch follows
+                    # the merge
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
+                    self._merge_all(state["par"])
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.route_events.append((state["e0"], e1))
+                    _lib.check(self.lib.t3d_event_record(self._done, h))
 
         self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, after_batch0,
                                            self._done, depth_is_u16, depth_scale, depth_max)

@@ -579,15 +579,16 @@ class TSDFVolume:
                                   depth_is_u16=False, depth_scale=1.0, depth_max=5.0, start=0):
         """integrate_sequence with the routing hooks of t3d_tsdf_integrate_sequence_hooked:
         nblocks_dev (int32[1] CUDA tensor) receives the block count after K4 of batch 0,
-        after_batch0(touch_event_handle, event_handle) is called on the host once K5 of batch 0 is enqueued
-        (the first event completes with K4 of batch 0, the second with K5 of batch 0), and the
+        after_batch0(phase, event_a, event_b) is called on the host twice — phase 0 once K5 of batch 0 is enqueued
+        (event_a completes with K4 of batch 0, event_b with K5 of batch 0), phase 1 once K4 of the last batch is
+        enqueued (event_a completes with it; the callee must record wait_event before returning) — and K5 of the
         last batch waits for wait_event (a handle from t3d_event_create)."""
         sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
         err = []
 
-        def _cb(_user, ev_touch, ev):
+        def _cb(_user, phase, ev_a, ev_b):
             try:
-                after_batch0(C.c_void_p(ev_touch), C.c_void_p(ev))
+                after_batch0(int(phase), C.c_void_p(ev_a), C.c_void_p(ev_b))
             except BaseException as e:  # noqa: BLE001 - must not propagate through the C frame
                 err.append(e)
         cb = _lib.SEQUENCE_HOOK(_cb)
