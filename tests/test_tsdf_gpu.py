@@ -317,7 +317,46 @@ def test_multi_gpu_routers_agree():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tests" / "mgpu_route_check.py")],
                        capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "p2p==nccl True owned==serial True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "p2p==nccl True owned==serial True overlapped==serial True" in r.stdout, \
+        r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_contexts_in_one_process(oracle):
+    """One process, one Context per GPU (needs >= 2 GPUs): per-device one-time initialisation (ICP neighbour
+    offsets in constant memory, the >48 KB shared-memory opt-in of the streaming back-projection kernel) must
+    happen on EACH device, and every entry point must select its context's device."""
+    import torch
+    from textureless_3d_reconstruction_b200.runtime import TSDFVolume, get_context
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    H, W = 240, 136
+    fr, K = frames(3, H, W)
+    ref = None
+    for dev in (0, 1, 0):
+        ctx = get_context(dev)
+        with torch.cuda.device(1 - dev):                 # the CURRENT device is deliberately the other one
+            d = torch.from_numpy(fr[0][0]).to(ctx.device)
+            c = torch.from_numpy(fr[0][1]).to(ctx.device)
+            pose = (fr[0][2][:, :3].copy(), fr[0][2][:, 3:4].copy())
+            # K1 streaming kernel (s = 1: needs the dynamic shared-memory attribute on this device)
+            xyz, rgb, n = ctx.backproject(d, c, fx=K[0], fy=K[1], cx=K[2], cy=K[3], pose=pose, max_depth=5.0)
+            n = int(n.item())
+            o_xyz, o_rgb = oracle.backproject(fr[0][0], fr[0][1], *K, pose=pose, max_depth=5.0)
+            assert n == len(o_xyz) and np.array_equal(rgb[:n].cpu().numpy(), o_rgb)
+            # TSDF + surface + ICP of the frame's own cloud against that surface (needs c_ofs on this device)
+            vol = TSDFVolume(0.01, 0.04, block_capacity=40000, ctx=ctx)
+            for dd, cc, T in fr:
+                vol.integrate(torch.from_numpy(dd).to(ctx.device), torch.from_numpy(cc).to(ctx.device), K, T, 1.0, 5.0)
+            p, nrm, _ = vol.extract_points(2.0)
+            src = xyz[:n:7].contiguous()
+            T0 = np.eye(4)
+            T0[0, 3] = 0.004
+            res = ctx.icp_point_to_plane(src, p.contiguous(), nrm.contiguous(), 0.05, init=T0, max_iter=30)
+            out = (vol.counters(), int(p.shape[0]), res.iterations, np.round(res.transformation, 9).tolist())
+        if ref is None:
+            ref = out
+        assert out == ref, (dev, out, ref)
+    assert ref[0]["voxel_updates"] > 10000 and abs(ref[3][0][3]) < 2e-3       # ICP pulled the offset back
 
 
 def test_full_size_tracking_properties(ctx):

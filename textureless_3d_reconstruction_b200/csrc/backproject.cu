@@ -45,6 +45,7 @@ struct BPParams {
   int W, s, Ws;
   int P;  // sampled pixels = Hs*Ws
   int has_pose, has_color;
+  int wide_bgr;  // colour frames are 4-byte aligned and a multiple of 4 bytes long: 32-bit colour loads are safe
   double scale, min_d, max_d;
   float scale32, min32, max32;
   float* out_xyz;
@@ -157,8 +158,19 @@ __global__ void __launch_bounds__(BP_THREADS, MINB)
       else d32[j] = __ldg(reinterpret_cast<const float*>(fr.depth) + sp);
       if (fr.conf != nullptr) cf[j] = __ldg(fr.conf + sp);
       if (p.has_color) {  // colour rides with the depth: pass B then has no DRAM loads
-        const uint8_t* c = fr.bgr + sp * 3;
-        crgb[j] = (uint32_t)__ldg(c + 2) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c) << 16);
+        if (p.wide_bgr) {
+          // the aligned 32-bit word that holds the pixel's first byte (+ the next word for the half of the pixels
+          // that reach into it) instead of three byte loads: a third of the L1 wavefronts per pixel
+          const unsigned long long o = (unsigned long long)sp * 3ull;
+          const unsigned* wp = reinterpret_cast<const unsigned*>(fr.bgr + (o & ~3ull));
+          const unsigned w0 = __ldg(wp);
+          unsigned w1 = 0u;
+          if ((o & 3ull) >= 2ull) w1 = __ldg(wp + 1);
+          crgb[j] = __byte_perm(__funnelshift_r(w0, w1, (unsigned)(o & 3ull) * 8u), 0u, 0x4012);  // b g r -> r | g<<8 | b<<16
+        } else {
+          const uint8_t* c = fr.bgr + sp * 3;
+          crgb[j] = (uint32_t)__ldg(c + 2) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c) << 16);
+        }
       }
       // advance (u,v) by 256 sampled pixels for the next j
       uu += BP_THREADS;
@@ -872,6 +884,8 @@ static int bp_launch(t3d_ctx* ctx, const t3d_backproject_params* q, const BPFram
     const char* e = getenv("T3D_K1_STREAM");
     use_stream = e ? atoi(e) : 1;
   }
+  p.wide_bgr = (q->has_color && ((long long)q->H * q->W * 3) % 4 == 0) ? 1 : 0;
+  for (int i = 0; i < n && p.wide_bgr; ++i) p.wide_bgr = ((uintptr_t)frames[i].bgr % 4 == 0) ? 1 : 0;
   bool stream = use_stream != 0 && s == 1 && q->W >= 4 && !q->depth_is_f64;
   for (int i = 0; i < n && stream; ++i) {
     const BPFrame& f = frames[i];
@@ -961,7 +975,7 @@ extern "C" int t3d_backproject(t3d_ctx* ctx, const void* depth, const uint8_t* b
                                void* out_rgb, int64_t capacity, int64_t* out_n,
                                t3d_stream stream) {
   T3D_REQUIRE(ctx && q && out_n, "t3d_backproject: null ctx/params/out_n");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(!q->has_color || bgr, "t3d_backproject: has_color but bgr is NULL");
   cudaStream_t st = as_stream(stream);
   int64_t P64 = 0;
@@ -994,7 +1008,7 @@ extern "C" int t3d_backproject_batch(t3d_ctx* ctx, const t3d_backproject_frame* 
                                      int64_t* out_offsets, t3d_stream stream) {
   T3D_REQUIRE(ctx && q && out_offsets && (n_frames == 0 || frames_h),
               "t3d_backproject_batch: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(n_frames >= 0, "t3d_backproject_batch: n_frames < 0");
   cudaStream_t st = as_stream(stream);
   int64_t P64 = 0;

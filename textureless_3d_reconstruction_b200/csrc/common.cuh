@@ -44,6 +44,27 @@ void t3d_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+// Every entry point runs on ITS context's device, whatever the caller's current device is (one process may
+// hold a context per GPU), and leaves the caller's current device as it found it.
+struct T3DDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit T3DDeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~T3DDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define T3D_ON_DEVICE(dev)            \
+  T3DDeviceGuard t3d_guard__(dev);    \
+  T3D_CUDA(t3d_guard__.err)
+
 // A grow-only device buffer owned by the ctx (scratch that survives calls so
 // the steady state does no cudaMalloc).
 struct DevBuf {

@@ -86,7 +86,7 @@ extern "C" int64_t t3d_launch_count(const t3d_ctx* ctx) {
 extern "C" int t3d_ipc_alloc(t3d_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t* handle_out64) {
   T3D_REQUIRE(ctx && dev_ptr && handle_out64 && bytes > 0, "t3d_ipc_alloc: bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   void* p = nullptr;
   T3D_CUDA(cudaMalloc(&p, bytes));
   cudaIpcMemHandle_t h;
@@ -104,7 +104,7 @@ extern "C" int t3d_ipc_alloc(t3d_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t
 
 extern "C" int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_ptr) {
   T3D_REQUIRE(ctx && handle64 && dev_ptr, "t3d_ipc_open: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   T3D_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -113,14 +113,14 @@ extern "C" int t3d_ipc_open(t3d_ctx* ctx, const uint8_t* handle64, void** dev_pt
 
 extern "C" int t3d_ipc_close(t3d_ctx* ctx, void* dev_ptr) {
   T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_close: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_CUDA(cudaIpcCloseMemHandle(dev_ptr));
   return T3D_OK;
 }
 
 extern "C" int t3d_ipc_free(t3d_ctx* ctx, void* dev_ptr) {
   T3D_REQUIRE(ctx && dev_ptr, "t3d_ipc_free: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_CUDA(cudaFree(dev_ptr));
   return T3D_OK;
 }

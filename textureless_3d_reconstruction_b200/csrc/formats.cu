@@ -118,7 +118,7 @@ int stream_grid(const t3d_ctx* ctx, long long n) {
 extern "C" int t3d_depth_u16_to_f32(t3d_ctx* ctx, const uint16_t* raw, int64_t n, float divisor,
                                     float* out, t3d_stream stream) {
   T3D_REQUIRE(ctx && n >= 0 && (n == 0 || (raw && out)) && divisor != 0.f, "t3d_depth_u16_to_f32: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   if (n == 0) return T3D_OK;
   u16_to_f32_kernel<<<stream_grid(ctx, n), 256, 0, as_stream(stream)>>>(raw, n, divisor, out);
   T3D_LAUNCH_CHECK();
@@ -129,7 +129,7 @@ extern "C" int t3d_depth_u16_to_f32(t3d_ctx* ctx, const uint16_t* raw, int64_t n
 extern "C" int t3d_depth_f32_to_u16(t3d_ctx* ctx, const float* depth, int64_t n, float factor,
                                     uint16_t* out, t3d_stream stream) {
   T3D_REQUIRE(ctx && n >= 0 && (n == 0 || (depth && out)), "t3d_depth_f32_to_u16: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   if (n == 0) return T3D_OK;
   f32_to_u16_kernel<<<stream_grid(ctx, n), 256, 0, as_stream(stream)>>>(depth, n, factor, out);
   T3D_LAUNCH_CHECK();
@@ -141,7 +141,7 @@ extern "C" int t3d_resize_bilinear_f32(t3d_ctx* ctx, const float* src, int src_h
                                        int dst_h, int dst_w, t3d_stream stream) {
   T3D_REQUIRE(ctx && src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0,
               "t3d_resize_bilinear_f32: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   const dim3 block(32, 8), grid((dst_w + 31) / 32, (dst_h + 7) / 8);
   resize_linear_kernel<<<grid, block, 0, as_stream(stream)>>>(src, src_h, src_w, dst, dst_h, dst_w,
                                                                (double)src_w / dst_w, (double)src_h / dst_h);
@@ -155,7 +155,7 @@ extern "C" int t3d_estimate_scale(t3d_ctx* ctx, const float* depth, int H, int W
                                   double* out_scale_h, int64_t* out_samples_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && depth && out_scale_h && H > 0 && W > 0 && n >= 0 && n < (1 << 24) &&
                   (n == 0 || (pts3d_h && pts2d_h)), "t3d_estimate_scale: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   *out_scale_h = 1.0;
   if (out_samples_h) *out_samples_h = 0;
   if (n < min_input_points || n == 0) return T3D_OK;  // der:673-674
@@ -188,7 +188,7 @@ extern "C" int t3d_estimate_scale(t3d_ctx* ctx, const float* depth, int H, int W
 extern "C" int t3d_pack_pointcloud2(t3d_ctx* ctx, const float* xyz, const void* colors, int colors_are_f32,
                                     int64_t n, float* out_records, t3d_stream stream) {
   T3D_REQUIRE(ctx && n >= 0 && (n == 0 || (xyz && colors && out_records)), "t3d_pack_pointcloud2: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   if (n == 0) return T3D_OK;
   cudaStream_t st = as_stream(stream);
   if (colors_are_f32)

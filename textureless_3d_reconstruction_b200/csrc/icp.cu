@@ -800,7 +800,7 @@ extern "C" int t3d_icp_linearize(t3d_ctx* ctx, const float* src, int64_t n_src, 
                                  const double* T_h, double* out27_h, double* out_stats_h,
                                  t3d_stream stream) {
   T3D_REQUIRE(ctx && T_h && out27_h && out_stats_h, "t3d_icp_linearize: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(max_corr_dist > 0.0, "t3d_icp_linearize: max_corr_dist must be > 0");
   for (int k = 0; k < 27; ++k) out27_h[k] = 0.0;
   out_stats_h[0] = out_stats_h[1] = 0.0;
@@ -825,7 +825,7 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
                                       double rel_fitness, double rel_rmse,
                                       t3d_icp_result* res, t3d_stream stream) {
   T3D_REQUIRE(ctx && res, "t3d_icp_point_to_plane: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(max_corr_dist > 0.0 && max_iter >= 0, "t3d_icp_point_to_plane: bad parameters");
   memset(res, 0, sizeof(*res));
   for (int i = 0; i < 16; ++i) res->T[i] = T0_h ? T0_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);
@@ -844,7 +844,7 @@ extern "C" int t3d_icp_point_to_plane_dev(t3d_ctx* ctx, const float* src, int64_
                                           int* skipped_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && res && src && tgt && tgt_nrm && n_src_dev && n_tgt_dev && src_capacity > 0 && tgt_capacity > 0,
               "t3d_icp_point_to_plane_dev: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(max_corr_dist > 0.0 && max_iter >= 0, "t3d_icp_point_to_plane_dev: bad parameters");
   memset(res, 0, sizeof(*res));
   for (int i = 0; i < 16; ++i) res->T[i] = T0_h ? T0_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);

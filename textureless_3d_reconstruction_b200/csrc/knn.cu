@@ -469,7 +469,7 @@ extern "C" int t3d_statistical_outlier(t3d_ctx* ctx, const double* xyz, int64_t 
                                        uint8_t* keep_mask, int64_t* out_kept, double* stats_h,
                                        t3d_stream stream) {
   T3D_REQUIRE(ctx && keep_mask && out_kept, "t3d_statistical_outlier: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(nb >= 1 && nb <= KMAX && std_ratio > 0.0,
               "t3d_statistical_outlier: nb_neighbors must be in [1,%d], std_ratio > 0", KMAX);
   cudaStream_t st = as_stream(stream);
@@ -540,7 +540,7 @@ static int sor_from_means(t3d_ctx* ctx, const double* mean, int64_t n, double st
 extern "C" int t3d_sor_mean_distances_part(t3d_ctx* ctx, const double* xyz, int64_t n, int nb, int part,
                                            int parts, double* out_mean_dist, t3d_stream stream) {
   T3D_REQUIRE(ctx && out_mean_dist && parts >= 1 && part >= 0 && part < parts, "t3d_sor_mean_distances_part: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(nb >= 1 && nb <= KMAX, "t3d_sor_mean_distances_part: nb_neighbors must be in [1,%d]", KMAX);
   if (n == 0) return T3D_OK;
   T3D_REQUIRE(xyz, "t3d_sor_mean_distances_part: null xyz");
@@ -565,7 +565,7 @@ extern "C" int t3d_sor_from_mean_distances(t3d_ctx* ctx, const double* mean_dist
                                            uint8_t* keep_mask, int64_t* out_kept, double* stats_h,
                                            t3d_stream stream) {
   T3D_REQUIRE(ctx && keep_mask && out_kept && std_ratio > 0.0, "t3d_sor_from_mean_distances: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   cudaStream_t st = as_stream(stream);
   T3D_CUDA(cudaMemsetAsync(out_kept, 0, sizeof(int64_t), st));
   if (n == 0) return T3D_OK;
@@ -576,7 +576,7 @@ extern "C" int t3d_sor_from_mean_distances(t3d_ctx* ctx, const double* mean_dist
 extern "C" int t3d_estimate_normals(t3d_ctx* ctx, const float* xyz, int64_t n, int knn,
                                     const double* orient_to_h, float* nrm, t3d_stream stream) {
   T3D_REQUIRE(ctx && (n == 0 || (xyz && nrm)), "t3d_estimate_normals: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(knn >= 1 && knn <= KMAX, "t3d_estimate_normals: knn must be in [1,%d]", KMAX);
   if (n == 0) return T3D_OK;
   cudaStream_t st = as_stream(stream);
@@ -599,7 +599,7 @@ extern "C" int t3d_nearest_neighbor(t3d_ctx* ctx, const float* query, int64_t n_
                                     const float* ref, int64_t n_ref, double radius,
                                     int32_t* out_idx, float* out_d2, t3d_stream stream) {
   T3D_REQUIRE(ctx && (n_q == 0 || (query && out_idx)), "t3d_nearest_neighbor: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(radius > 0.0, "t3d_nearest_neighbor: radius must be > 0");
   if (n_q == 0) return T3D_OK;
   cudaStream_t st = as_stream(stream);

@@ -136,7 +136,7 @@ extern "C" int t3d_synth_frame(t3d_ctx* ctx, int scene, int frame_index, int H, 
                                double fy, double cx, double cy, uint64_t seed, float noise_sigma,
                                float* depth, uint8_t* bgr, double* T_cw_h, t3d_stream stream) {
   T3D_REQUIRE(ctx, "t3d_synth_frame: null ctx");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(scene == 0 || scene == 1, "t3d_synth_frame: unknown scene %d", scene);
   T3D_REQUIRE(H > 0 && W > 0, "t3d_synth_frame: bad size");
   SynthParams p;

@@ -645,7 +645,7 @@ int t3d_radix_sort_u64(t3d_ctx* ctx, unsigned long long* keys_a, unsigned* vals_
 extern "C" int t3d_bounds(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, int64_t n,
                           double* min_h, double* max_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && min_h && max_h, "t3d_bounds: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(n > 0 && xyz, "t3d_bounds: empty cloud");
   cudaStream_t st = as_stream(stream);
   const int grid = ctx->num_sms * 16;
@@ -679,7 +679,7 @@ static int voxel_run(t3d_ctx* ctx, const void* xyz, int xyz_is_f64, const uint8_
                      int32_t* out_vox_idx, VoxRec* part_out, int part_world, int32_t* part_counts,
                      int64_t capacity, int64_t* out_m, double* out_min_bound_h, t3d_stream stream) {
   T3D_REQUIRE(ctx && out_m, "t3d_voxel_downsample: null argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   T3D_REQUIRE(voxel > 0.0, "t3d_voxel_downsample: voxel_size <= 0");  // Open3D raises
   cudaStream_t st = as_stream(stream);
   if (part_out) T3D_CUDA(cudaMemsetAsync(part_counts, 0, sizeof(int32_t) * (size_t)part_world, st));
@@ -889,7 +889,7 @@ extern "C" int t3d_compact_rows(t3d_ctx* ctx, const void* rows, int64_t n, int32
                                 const uint8_t* keep_mask, void* out_rows, int64_t* out_n,
                                 t3d_stream stream) {
   T3D_REQUIRE(ctx && out_n && row_bytes > 0, "t3d_compact_rows: bad argument");
-  T3D_CUDA(cudaSetDevice(ctx->device));
+  T3D_ON_DEVICE(ctx->device);
   cudaStream_t st = as_stream(stream);
   if (n == 0) {
     T3D_CUDA(cudaMemsetAsync(out_n, 0, sizeof(int64_t), st));

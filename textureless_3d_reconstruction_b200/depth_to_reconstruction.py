@@ -252,9 +252,12 @@ class DepthToReconstructionPipeline:
         self.camera_poses = []
         prev_cam_cloud = None
         T_wc = np.eye(4)  # camera -> world of the current frame
+        ds, cs = [], []
         for i, (img, depth) in enumerate(zip(self.images, self.depths)):
             d = torch.from_numpy(np.ascontiguousarray(depth, np.float32)).to(dev)
             c = torch.from_numpy(np.ascontiguousarray(img, np.uint8)).to(dev)
+            ds.append(d)
+            cs.append(c)
             if self.given_poses is not None:
                 pose = self.given_poses[i]
             else:
@@ -268,13 +271,31 @@ class DepthToReconstructionPipeline:
                 T_cw = np.linalg.inv(T_wc)
                 pose = (np.ascontiguousarray(T_cw[:3, :3]), np.ascontiguousarray(T_cw[:3, 3:4]))
             self.camera_poses.append(pose)
-            xyz, rgb = self.dense.depth_to_pointcloud_device(d, c, pose=pose, scale=1.0, subsample=s)
-            all_xyz.append(xyz)
-            all_rgb.append(rgb)
-            print(f"Camera {i}: {xyz.shape[0]} points" if i < 2 else f"  Camera {i}: {xyz.shape[0]} points")
+        same_size = all(d.shape == ds[0].shape for d in ds)
+        if same_size:
+            # the per-frame loop of d2r:566-658 as ONE batched call (32 frames per launch, frame-ordered output ==
+            # the reference's list + np.vstack): no launch and no host sync per frame; the per-camera counts come
+            # back with a single read of the offsets
+            H, W = ds[0].shape
+            frames = ctx.make_backproject_frames(ds, cs, self.camera_poses)
+            xyz, rgb, offs = ctx.backproject_batch(
+                frames, len(ds), H, W, fx=self.config.fx, fy=self.config.fy, cx=self.config.cx, cy=self.config.cy,
+                subsample=s, scale=1.0, min_depth=self.config.min_depth, max_depth=self.config.max_depth)
+            offs = offs.cpu().tolist()
+            all_xyz, all_rgb = [xyz[:offs[-1]]], [rgb[:offs[-1]]]
+            counts = [offs[i + 1] - offs[i] for i in range(len(ds))]
+        else:
+            counts = []
+            for d, c, pose in zip(ds, cs, self.camera_poses):
+                xyz, rgb = self.dense.depth_to_pointcloud_device(d, c, pose=pose, scale=1.0, subsample=s)
+                all_xyz.append(xyz)
+                all_rgb.append(rgb)
+                counts.append(xyz.shape[0])
+        for i, n in enumerate(counts):
+            print(f"Camera {i}: {n} points" if i < 2 else f"  Camera {i}: {n} points")
         print("\n--- Step 5: Merge and clean point cloud ---")
-        pts = torch.cat(all_xyz).contiguous()
-        cols = torch.cat(all_rgb).contiguous()
+        pts = (all_xyz[0] if len(all_xyz) == 1 else torch.cat(all_xyz)).contiguous()
+        cols = (all_rgb[0] if len(all_rgb) == 1 else torch.cat(all_rgb)).contiguous()
         if pts.shape[0] == 0:
             return np.array([]), np.array([]), self.camera_poses
         if self.config.voxel_size > 0:
