@@ -16,7 +16,17 @@
  *     asynchronous w.r.t. the host unless documented otherwise.
  *   - Return value: 0 = OK, negative = error (T3D_E_*).  t3d_last_error()
  *     returns a thread-local message.  No exceptions cross the boundary.
- *   - One t3d_ctx per process/GPU.  A ctx is not thread-safe; distinct ctxs are.
+ *   - One t3d_ctx per GPU; a process may hold several (one per device).  Every
+ *     entry point runs on ITS ctx's device whatever the caller's current device
+ *     is, and restores the caller's current device before it returns.  A ctx is
+ *     not thread-safe; distinct ctxs are.
+ *   - ONE STREAM AT A TIME PER CTX: a ctx owns scratch that its asynchronous
+ *     launches share (scan / ticket state of K1, the cached projection tables,
+ *     hash tables and partials of K2/K3/K8).  Calls on the same ctx must be
+ *     issued on one stream, or be ordered across streams by the caller (event
+ *     or synchronise) — the library adds no cross-stream ordering of its own.
+ *     A t3d_tsdf volume is the same: its sequence calls use one internal side
+ *     stream that is ordered against the caller's stream on entry and exit.
  *   - There is NO CPU fallback: without a CUDA device every compute call
  *     returns T3D_E_CUDA.
  */
