@@ -249,19 +249,19 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
                                 int depth_is_u16, float depth_scale,
                                 float depth_max, t3d_stream stream);
 
-/* The same pipeline with hooks, for block routing that overlaps fusion (callers put
- * the frames whose blocks must travel into batch 0 and the frames that meet incoming blocks
- * into the last batch):
- *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch 0 — every
- *     block batch 0 touches exists and no allocation is in flight at that point;
- *   after_batch0(user, phase, event_a, event_b): called ON THE HOST, inside this call, twice:
- *     phase 0, right after K5 of batch 0 was enqueued: event_a (a cudaEvent_t) completes with K4 of batch 0
- *       (from then on nblocks_after_touch0 and the keys of those blocks are final), event_b with K5 of
- *       batch 0.  The callee enqueues its own work on another stream (t3d_stream_wait_event);
- *     phase 1, right after K4 of the LAST batch was enqueued: event_a completes with it (event_b is NULL).
- *       The callee enqueues what must run between K4 and K5 of the last batch (the merge of incoming
- *       blocks: it allocates blocks like K4 does, so it is ordered after it) and records its completion
- *       event, wait_before_last, before returning;
+/* The same pipeline with hooks, for block routing that overlaps fusion.  The caller orders the
+ * frames so that every frame whose blocks must travel is in batches 0..hook_batch, and every frame that meets
+ * incoming blocks is either in those batches too (then the merge needs no ordering against later batches) or in
+ * the last batch (then wait_before_last orders it):
+ *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch `hook_batch` — every block
+ *     batches 0..hook_batch touch exists and no allocation is in flight at that point;
+ *   after_batch0(user, phase, event_a, event_b): called ON THE HOST, inside this call:
+ *     phase 0, right after K5 of batch `hook_batch` was enqueued: event_a (a cudaEvent_t) completes with K4 of that
+ *       batch (from then on nblocks_after_touch0 and the keys of those blocks are final), event_b with its K5.  The
+ *       callee enqueues its own work on another stream (t3d_stream_wait_event);
+ *     phase 1, only when wait_before_last is given, right after K4 of the LAST batch was enqueued: event_a completes
+ *       with it (event_b is NULL).  The callee enqueues what must run between K4 and K5 of the last batch and records
+ *       wait_before_last before returning;
  *   wait_before_last (cudaEvent_t, nullable): K5 of the last batch waits for it (without a hook: K4 too).
  * Needs at least 2 batches when any hook is given. */
 typedef void (*t3d_sequence_hook)(void* user, int phase, void* event_a, void* event_b);
@@ -270,7 +270,7 @@ int t3d_tsdf_integrate_sequence_hooked(t3d_tsdf* v, const t3d_frame_view* frames
                                        int depth_is_u16, float depth_scale, float depth_max,
                                        int32_t* nblocks_after_touch0,
                                        t3d_sequence_hook after_batch0, void* user,
-                                       void* wait_before_last, t3d_stream stream);
+                                       void* wait_before_last, int hook_batch, t3d_stream stream);
 /* Timing-less CUDA events for the hooks above (handles are cudaEvent_t). */
 int t3d_event_create(void** out_event);
 int t3d_event_destroy(void* event);

@@ -101,6 +101,9 @@ def main():
     rs = D.P2PBlockRouter(vs, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
     order = D.P2PBlockRouter.overlap_order(F2, B2)
     views_o = vo.make_frame_views([dd[i] for i in order], [cc[i] for i in order], [K] * F2, [fr[i][2] for i in order])
+    order_c = D.P2PBlockRouter.head_tail_order(F2, B2)
+    assert sorted(order_c) == list(range(F2)) and order_c[:B2] == list(range(B2)) and order_c[B2:2 * B2] == list(range(F2 - B2, F2))
+    views_c = vc.make_frame_views([dd[i] for i in order_c], [cc[i] for i in order_c], [K] * F2, [fr[i][2] for i in order_c])
     views_s = vs.make_frame_views(dd, cc, [K] * F2, [f[2] for f in fr])
     ok3 = True
     for rep in range(3):                                   # both receive buffers, steady state
@@ -108,7 +111,7 @@ def main():
         vc.reset()
         vs.reset()
         ro.fuse_overlapped(views_o, F2, H, W, B2, False, 1.0, 5.0)
-        rc.fuse_overlapped(views_o, F2, H, W, B2, False, 1.0, 5.0)
+        rc.fuse_overlapped(views_c, F2, H, W, B2, False, 1.0, 5.0)
         vs.integrate_sequence(views_s, F2, H, W, B2, False, 1.0, 5.0)
         rs.route()
         torch.cuda.synchronize()
@@ -120,7 +123,7 @@ def main():
         ok3 = ok3 and np.array_equal(eo[0], es[0]) and np.array_equal(eo[2], es[2])      # keys, integer weights
         ok3 = ok3 and float(np.abs(eo[1] - es[1]).max()) < 1e-4 and ro.stats()[1] == 0 and ro.stats()[0] == rs.stats()[0]
         ok3 = ok3 and np.array_equal(ec[0], eo[0]) and np.array_equal(ec[2], eo[2])      # copy-engine == peer-store
-        ok3 = ok3 and np.array_equal(ec[1].view(np.uint32), eo[1].view(np.uint32)) and rc.stats()[0] == ro.stats()[0]
+        ok3 = ok3 and float(np.abs(ec[1] - eo[1]).max()) < 1e-4 and rc.stats()[0] == ro.stats()[0]   # other frame order: rounding
     ref2 = TSDFVolume(0.01, 0.04, block_capacity=480000, ctx=ctx)
     for r in range(world):
         for i in range(F2):

@@ -104,7 +104,7 @@ _SIGS = {
     "t3d_memcpy_async": (_I, [_VP, _VP, C.c_size_t, _VP]),
     "t3d_tsdf_route_export_p2p": (_I, [_VP, _I, C.c_int32, _I, _I, _VP, _VP, _I64, _VP, _VP, _VP]),
     "t3d_tsdf_integrate_sequence_hooked": (_I, [_VP, C.POINTER(FrameView), _I, _I, _I, _I, _I, _F, _F, _VP,
-                                                SEQUENCE_HOOK, _VP, _VP, _VP]),
+                                                SEQUENCE_HOOK, _VP, _VP, _I, _VP]),
     "t3d_event_create": (_I, [C.POINTER(_VP)]),
     "t3d_event_destroy": (_I, [_VP]),
     "t3d_event_record": (_I, [_VP, _VP]),
