@@ -271,7 +271,7 @@ def run_ours(args):
                and -(-F // B) >= 3 and B >= int(np.ceil(DEPTH_MAX / 0.25)) + 2)
     views_ov = None
     if overlap:
-        order = (P2PBlockRouter.head_tail_order if args.router == "ce" else P2PBlockRouter.overlap_order)(F, B)
+        order = (P2PBlockRouter.tail_head_order if args.router == "ce" else P2PBlockRouter.overlap_order)(F, B)
         views_ov = vol.make_frame_views([depth_all[i] for i in order], [bgr_all[i] for i in order],
                                         [KINTR] * F, [poses[i] for i in order])
 
@@ -349,9 +349,9 @@ def run_ours(args):
                        "route_ms_note": "CUDA events on the router's stream around count/pack/copies/fence/merge"
                                         + (" (runs underneath fusion)" if overlap else ""),
                        "overlapped_with_fusion": bool(overlap),
-                       "batch_order": (("head batch (the frames that meet incoming blocks) first, tail batch (the frames whose "
-                                        "blocks travel) second, routing on a side stream underneath the middle batches; "
-                                        "nothing in the fusion waits for the merge" if args.router == "ce" else
+                       "batch_order": (("tail batch (the frames whose blocks travel) first, head batch (the frames that meet "
+                                        "incoming blocks) second, routing on a side stream underneath everything after the "
+                                        "tail; nothing in the fusion waits for the merge" if args.router == "ce" else
                                         "last batch (frames that reach past the slab) first, routing on a side stream "
                                         "underneath the other batches, first batch last after the merge")
                                        if overlap else "ascending, routing after fusion"),

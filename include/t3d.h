@@ -256,12 +256,12 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
  *   nblocks_after_touch0 (device int32, nullable): the block count after K4 of batch `hook_batch` — every block
  *     batches 0..hook_batch touch exists and no allocation is in flight at that point;
  *   after_batch0(user, phase, event_a, event_b): called ON THE HOST, inside this call:
- *     phase 0, right after K5 of batch `hook_batch` was enqueued: event_a (a cudaEvent_t) completes with K4 of that
- *       batch (from then on nblocks_after_touch0 and the keys of those blocks are final), event_b with its K5.  The
- *       callee enqueues its own work on another stream (t3d_stream_wait_event);
- *     phase 1, only when wait_before_last is given, right after K4 of the LAST batch was enqueued: event_a completes
- *       with it (event_b is NULL).  The callee enqueues what must run between K4 and K5 of the last batch and records
- *       wait_before_last before returning;
+ *     phase b >= hook_batch, right after K5 of batch b was enqueued: event_a (a cudaEvent_t) completes with K4 of
+ *       that batch (for b == hook_batch: from then on nblocks_after_touch0 and the keys of those blocks are final),
+ *       event_b with its K5.  The callee enqueues its own work on another stream (t3d_stream_wait_event);
+ *     phase -1, only when wait_before_last is given, right after K4 of the LAST batch was enqueued: event_a
+ *       completes with it (event_b is NULL).  The callee enqueues what must run between K4 and K5 of the last batch
+ *       and records wait_before_last before returning;
  *   wait_before_last (cudaEvent_t, nullable): K5 of the last batch waits for it (without a hook: K4 too).
  * Needs at least 2 batches when any hook is given. */
 typedef void (*t3d_sequence_hook)(void* user, int phase, void* event_a, void* event_b);

@@ -101,8 +101,8 @@ def main():
     rs = D.P2PBlockRouter(vs, rank, world, slab_frames=F2, frame_advance=0.25, block_size=0.08, region_records=16384)
     order = D.P2PBlockRouter.overlap_order(F2, B2)
     views_o = vo.make_frame_views([dd[i] for i in order], [cc[i] for i in order], [K] * F2, [fr[i][2] for i in order])
-    order_c = D.P2PBlockRouter.head_tail_order(F2, B2)
-    assert sorted(order_c) == list(range(F2)) and order_c[:B2] == list(range(B2)) and order_c[B2:2 * B2] == list(range(F2 - B2, F2))
+    order_c = D.P2PBlockRouter.tail_head_order(F2, B2)
+    assert sorted(order_c) == list(range(F2)) and order_c[:B2] == list(range(F2 - B2, F2)) and order_c[B2:2 * B2] == list(range(B2))
     views_c = vc.make_frame_views([dd[i] for i in order_c], [cc[i] for i in order_c], [K] * F2, [fr[i][2] for i in order_c])
     views_s = vs.make_frame_views(dd, cc, [K] * F2, [f[2] for f in fr])
     ok3 = True

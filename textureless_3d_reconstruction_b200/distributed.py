@@ -227,15 +227,15 @@ class P2PBlockRouter:
     # incoming blocks (the slab's first frames) is fused LAST, after the merge.  Unit-weight running
     # means do not depend on the order in which frames arrive (weights exact, tsdf to rounding).
     @staticmethod
-    def head_tail_order(n_frames, batch):
-        """Frame order of CopyEngineBlockRouter.fuse_overlapped: the HEAD batch (the slab's first frames, the only ones
-        that meet incoming blocks) first, the TAIL batch (the only frames whose blocks travel) second, the middle
+    def tail_head_order(n_frames, batch):
+        """Frame order of CopyEngineBlockRouter.fuse_overlapped: the TAIL batch (the only frames whose blocks travel)
+        first, the HEAD batch (the slab's first frames, the only ones that meet incoming blocks) second, the middle
         batches after them; frames ascending inside a batch."""
         head = list(range(0, min(batch, n_frames)))
         tail_lo = max(len(head), n_frames - batch)
         tail = list(range(tail_lo, n_frames))
         middle = list(range(len(head), tail_lo))
-        return head + tail + middle
+        return tail + head + middle
 
     @staticmethod
     def overlap_order(n_frames, batch):
@@ -274,7 +274,7 @@ class P2PBlockRouter:
                 if phase == 0:      # behind K5 of batch 0: export + fence, underneath the middle batches
                     _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
                     state["par"] = self._export(self._snap)
-                else:               # behind K4 of the last batch (both allocate blocks): merge, then K5 of the last batch
+                elif phase == -1:   # behind K4 of the last batch (both allocate blocks): merge, then K5 of the last batch
                     _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
                     self._merge(state["par"])
                     _lib.check(self.lib.t3d_event_record(self._done, h))
@@ -405,11 +405,11 @@ class CopyEngineBlockRouter(P2PBlockRouter):
 
     def fuse_overlapped(self, views_reordered, n_frames, H, W, batch, depth_is_u16=False, depth_scale=1.0,
                         depth_max=5.0, frame_advance=0.25):
-        """Fuse `views_reordered` (frame views in head_tail_order) and route in the same pass.  Batch 0 is the slab's
-        head (the only frames that meet incoming blocks), batch 1 its tail (the only frames whose blocks travel):
-        count / pack / copies / fence / merge are enqueued on the router's stream behind K5 of batch 1 and run
-        underneath the middle batches.  NOTHING in the fusion waits for them — by the time the merge touches an
-        incoming block, the head batch is long done and no later batch reaches it — only the end of the step does.
+        """Fuse `views_reordered` (frame views in tail_head_order) and route in the same pass.  Batch 0 is the slab's
+        tail (the only frames whose blocks travel), batch 1 its head (the only frames that meet incoming blocks):
+        count / pack / copies / fence are enqueued on the router's stream behind K5 of batch 0 and run underneath the
+        other batches; the merge follows K5 of batch 1.  NOTHING in the fusion waits for the routing — no later batch
+        reaches an incoming block — only the end of the step does, so the route has the whole step to hide in.
         The current stream ends ordered after fusion AND routing."""
         import torch
         from . import _lib
@@ -425,27 +425,33 @@ class CopyEngineBlockRouter(P2PBlockRouter):
             _lib.check(self.lib.t3d_event_create(C.byref(self._done)))
             self._snap = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
         side = self._side
+        state = {}
 
-        def after_tail(phase, ev_a, ev_b):
-            if phase != 0:
-                return
+        def hook(phase, ev_a, ev_b):
             h = C.c_void_p(side.cuda_stream)
-            with torch.cuda.stream(side):
-                # the blocks that will travel exist once K4 of the tail batch is done: count them (host read) while its
-                # K5 is still running ...
-                _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
-                counts = self._read_counts(self._snap)
-                # ... and pack / copy / fence / merge behind that K5, underneath the fusion of the middle batches
-                _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                self._merge_all(self._send(counts, self._snap))
-                e1.record()
-                self.route_events.append((e0, e1))
-            _lib.check(self.lib.t3d_event_record(self._done, h))
+            if phase == 0:
+                with torch.cuda.stream(side):
+                    # the blocks that will travel exist once K4 of the tail batch is done: count them (host read) while
+                    # its K5 is still running ...
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
+                    counts = self._read_counts(self._snap)
+                    # ... and pack / copy / fence behind that K5, underneath the fusion of the other batches
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
+                    state["e0"] = torch.cuda.Event(enable_timing=True)
+                    state["e0"].record()
+                    state["par"] = self._send(counts, self._snap)
+            elif phase == 1:
+                with torch.cuda.stream(side):
+                    # the head batch is the only one that touches incoming blocks: merge once its K5 is done
+                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
+                    self._merge_all(state["par"])
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.route_events.append((state["e0"], e1))
+                _lib.check(self.lib.t3d_event_record(self._done, h))
 
-        self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, after_tail, None,
-                                           depth_is_u16, depth_scale, depth_max, hook_batch=1)
+        self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, hook, None,
+                                           depth_is_u16, depth_scale, depth_max, hook_batch=0)
         _lib.check(self.lib.t3d_stream_wait_event(_stream(), self._done))
 
     def stats(self):

@@ -579,10 +579,10 @@ class TSDFVolume:
                                   depth_is_u16=False, depth_scale=1.0, depth_max=5.0, start=0, hook_batch=0):
         """integrate_sequence with the routing hooks of t3d_tsdf_integrate_sequence_hooked:
         nblocks_dev (int32[1] CUDA tensor) receives the block count after K4 of batch `hook_batch`,
-        after_batch0(phase, event_a, event_b) is called on the host — phase 0 once K5 of batch `hook_batch` is enqueued
-        (event_a completes with K4 of that batch, event_b with its K5) and, only if wait_event is given, phase 1 once K4
-        of the last batch is enqueued (event_a completes with it; the callee must record wait_event before returning;
-        K5 of the last batch waits for wait_event, a handle from t3d_event_create)."""
+        after_batch0(phase, event_a, event_b) is called on the host — phase b (every b >= hook_batch) once K5 of batch b
+        is enqueued (event_a completes with K4 of that batch, event_b with its K5) and, only if wait_event is given,
+        phase -1 once K4 of the last batch is enqueued (event_a completes with it; the callee must record wait_event
+        before returning; K5 of the last batch waits for wait_event, a handle from t3d_event_create)."""
         sub = C.cast(C.byref(views, start * C.sizeof(FrameView)), C.POINTER(FrameView))
         err = []
 
