@@ -268,20 +268,33 @@ class Context:
         n = xyz.shape[0]
         dev = xyz.device
         assert xyz.is_contiguous()
-        cap = int(capacity) if capacity is not None else n
-        o_xyz = torch.empty((max(cap, 1), 3), dtype=torch.float64, device=dev)
-        o_rgb = torch.empty((max(cap, 1), 3), dtype=torch.uint8, device=dev) if rgb is not None else None
-        o_sum = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if rgb is not None else None
-        o_cnt = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
-        o_idx = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if want_idx else None
-        o_m = torch.zeros(1, dtype=torch.int64, device=dev)
-        mb_in = None if min_bound is None else np.ascontiguousarray(min_bound, np.float64)
-        mb_out = np.zeros(3, np.float64)
-        check(self.lib.t3d_voxel_downsample(
-            self.handle, _ptr(xyz), int(xyz.dtype == torch.float64), _ptr(rgb), n, float(voxel_size),
-            _np_ptr(mb_in), int(bool(sorted_output)), _ptr(o_xyz), _ptr(o_rgb), _ptr(o_sum), _ptr(o_cnt),
-            _ptr(o_idx), cap, _ptr(o_m), _np_ptr(mb_out), _stream()))
+        # The outputs hold one row per VOXEL, which is known only after the first pass.  Allocating them for the worst
+        # case (one voxel per point: 59 bytes x N, half a gigabyte for a merged cloud) costs more than the kernels, so the
+        # first attempt sizes them from the last call's ratio (1/4 of N the first time); the library reports
+        # T3D_E_CAPACITY after its first pass (before anything is written) if that was too small, and the call is redone
+        # with the worst case.
+        ratio = getattr(self, "_k2_ratio", 0.25)
+        attempts = [int(capacity)] if capacity is not None else [min(n, max(int(n * ratio * 1.25) + 1024, 4096)), n]
+        for cap in attempts:
+            o_xyz = torch.empty((max(cap, 1), 3), dtype=torch.float64, device=dev)
+            o_rgb = torch.empty((max(cap, 1), 3), dtype=torch.uint8, device=dev) if rgb is not None else None
+            o_sum = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if rgb is not None else None
+            o_cnt = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+            o_idx = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev) if want_idx else None
+            o_m = torch.zeros(1, dtype=torch.int64, device=dev)
+            mb_in = None if min_bound is None else np.ascontiguousarray(min_bound, np.float64)
+            mb_out = np.zeros(3, np.float64)
+            rc = self.lib.t3d_voxel_downsample(
+                self.handle, _ptr(xyz), int(xyz.dtype == torch.float64), _ptr(rgb), n, float(voxel_size),
+                _np_ptr(mb_in), int(bool(sorted_output)), _ptr(o_xyz), _ptr(o_rgb), _ptr(o_sum), _ptr(o_cnt),
+                _ptr(o_idx), cap, _ptr(o_m), _np_ptr(mb_out), _stream())
+            if rc == _lib.T3D_E_CAPACITY and cap < n and capacity is None:
+                continue
+            check(rc)
+            break
         m = int(o_m.item())
+        if n > 0:
+            self._k2_ratio = max(m / n, 1e-3)
         return dict(points=o_xyz[:m], colors=None if o_rgb is None else o_rgb[:m],
                     rgb_sum=None if o_sum is None else o_sum[:m], count=o_cnt[:m],
                     idx=None if o_idx is None else o_idx[:m], min_bound=mb_out, m=m)
@@ -325,6 +338,8 @@ class Context:
                                                 _ptr(o_rgb), _ptr(o_sum), _ptr(o_cnt), _ptr(o_idx), cap, _ptr(o_m),
                                                 _stream()))
         m = int(o_m.item())
+        if n > 0:
+            self._k2_ratio = max(m / n, 1e-3)
         return dict(points=o_xyz[:m], colors=None if o_rgb is None else o_rgb[:m],
                     rgb_sum=None if o_sum is None else o_sum[:m], count=o_cnt[:m], idx=o_idx[:m],
                     min_bound=mb, m=m)
