@@ -466,6 +466,15 @@ int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_src,
                            double rel_fitness, double rel_rmse,
                            t3d_icp_result* result_h, t3d_stream stream);
 
+/* The correspondence search of the device-resident registration on its own (the kernel R8's iterations spend
+ * their time in): for every source point the ORIGINAL index of the nearest target point within max_corr_dist of
+ * T0 * p (-1: none; ties -> lowest index) and the squared distance (f64).  With T1 != NULL a second search at T1,
+ * seeded with the first one's answers exactly as a registration's later iterations are, replaces the result.
+ * Replaces: open3d KDTreeFlann::SearchHybrid(knn = 1) inside registration_icp. */
+int t3d_icp_correspondences(t3d_ctx* ctx, const float* src, int64_t n_src, const float* tgt, const float* tgt_nrm,
+                            int64_t n_tgt, double max_corr_dist, const double* T0_h, const double* T1_h,
+                            int32_t* out_idx, double* out_d2, t3d_stream stream);
+
 /* Same registration with the cloud sizes in DEVICE memory (int64): src/tgt buffers hold up
  * to src_capacity / tgt_capacity points, of which *n_src_dev / *n_tgt_dev are valid.  Made for
  * frame-to-model tracking, where both clouds were just produced on the device (K1, K6): their

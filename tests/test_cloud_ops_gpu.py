@@ -162,6 +162,53 @@ def test_icp_vs_oracle(ctx, oracle):
     assert np.array_equal(idx.cpu().numpy(), oi)
 
 
+def _brute_nn(src, tgt, T, r):
+    """Exact reference of the registration's search: q = T p accumulated left to right in f64, candidates from a
+    KD-tree (8 nearest), d2 = (dx^2 + dy^2) + dz^2 in f64, smallest (d2, index) within r."""
+    from scipy.spatial import cKDTree
+    p = src.astype(np.float64)
+    q = np.stack([((T[k, 0] * p[:, 0] + T[k, 1] * p[:, 1]) + T[k, 2] * p[:, 2]) + T[k, 3] for k in range(3)], 1)
+    t64 = tgt.astype(np.float64)
+    _, cand = cKDTree(t64).query(q, k=8)
+    d = t64[cand] - q[:, None, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    order = np.lexsort((cand, d2), axis=1)[:, 0]
+    rows = np.arange(len(q))
+    idx, best = cand[rows, order], d2[rows, order]
+    ok = best <= r * r
+    return np.where(ok, idx, -1).astype(np.int32), np.where(ok, best, r * r)
+
+
+@pytest.mark.parametrize("offset", [0.0, 31.0, 900.0])
+def test_icp_search_equals_brute_force(ctx, offset):
+    """icp_nn_kernel (f32 rejection tests, f64 decision) against an exact f64 reference: a noisy surface with
+    coordinates up to `offset` metres (the f32 rounding of the query grows with them), cold and warm-seeded."""
+    import torch
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(np.arange(420), np.arange(400)), -1).reshape(-1, 2) * 0.01
+    tgt = np.column_stack([g[:, 0], g[:, 1], 0.3 * np.sin(3 * g[:, 0]) + 0.2 * np.cos(2 * g[:, 1])])
+    tgt = (tgt + rng.normal(0, 0.002, tgt.shape) + offset).astype(np.float32)
+    tgt[1000:1200] = tgt[3000:3200]                                      # exact duplicates: ties -> lowest index
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (len(tgt), 1))
+    sel = rng.choice(len(tgt), 40000, replace=False)
+    src = (tgt[sel] + rng.normal(0, 0.004, (len(sel), 3))).astype(np.float32)
+    src[:300] += 0.2                                                      # some queries without a correspondence
+    src[300:400] = tgt[sel[300:400]]                                      # zero-distance queries
+    a = 0.002
+    T0 = np.eye(4); T0[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    c = tgt.mean(0).astype(np.float64)
+    T0[:3, 3] = c - T0[:3, :3] @ c + [0.004, -0.003, 0.002]               # small motion about the cloud centre
+    T1 = T0.copy(); T1[:3, 3] += [-0.003, 0.002, 0.001]
+    S, Tg, Ng = (torch.from_numpy(x).cuda() for x in (src, tgt, nrm))
+    for Ta, Tb in ((T0, None), (T0, T1)):
+        idx, d2 = ctx.icp_correspondences(S, Tg, Ng, 0.05, Ta, Tb)
+        ri, rd = _brute_nn(src, tgt, Ta if Tb is None else Tb, 0.05)
+        idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+        assert np.array_equal(idx, ri), (offset, Tb is not None, int((idx != ri).sum()))
+        assert np.array_equal(d2[ri >= 0], rd[ri >= 0])
+    assert (ri >= 0).mean() > 0.9 and (ri < 0).sum() >= 200
+
+
 def test_ply_writers(tmp_path):
     """K9 host writers: reference ASCII layout byte-for-byte vs the reference's own file;
     Open3D binary layout structurally (R9)."""

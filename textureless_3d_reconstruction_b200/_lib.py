@@ -123,6 +123,7 @@ _SIGS = {
     "t3d_write_ply_mesh_h": (_I, [C.c_char_p, _VP, _VP, _VP, _I64, _VP, _I64]),
     "t3d_estimate_normals": (_I, [_VP, _VP, _I64, _I, _VP, _VP, _VP]),
     "t3d_icp_point_to_plane": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _I, _D, _D, C.POINTER(IcpResult), _VP]),
+    "t3d_icp_correspondences": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP]),
     "t3d_icp_point_to_plane_dev": (_I, [_VP, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I, _D, _VP, _I, _D, _D,
                                         C.POINTER(IcpResult), C.POINTER(C.c_int), _VP]),
     "t3d_icp_linearize": (_I, [_VP, _VP, _I64, _VP, _VP, _I64, _D, _VP, _VP, _VP, _VP]),

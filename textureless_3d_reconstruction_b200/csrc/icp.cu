@@ -299,23 +299,58 @@ __global__ void hg_scatter_kernel(const float* __restrict__ tgt, const float* __
 // Exact: cells are visited ring by ring around the query's cell; a cell is skipped
 // only if its box is farther than the best distance so far, and the search stops
 // after ring k once best <= (k*h + distance of q to its own cell's faces)^2.
+//
+// The result is decided in f64 (the oracle's arithmetic), but nearly every candidate and cell is
+// REJECTED in f32: a candidate's f32 squared distance to the f32-rounded query differs from the exact
+// one by at most M (nn_margin), so `d2f > best + M` proves it cannot beat or tie the incumbent; only the
+// survivors (the eventual answer and its near-ties) pay the f32->f64 conversions and the f64 chain.
+// Cell boxes are tested the same way with their own error bound.  Rejecting less is always safe.
 struct NNState {
   double best;
   int bj;
   unsigned bo;
+  float thr;      // candidates with an f32 squared distance above this cannot win
+  float thr_box;  // cells whose f32 box distance exceeds this cannot hold a winner
 };
 
-// squared distance from the query (offset (lx,ly,lz) inside its own cell) to the box of the
-// cell at integer offset (dx,dy,dz)
-__device__ __forceinline__ double hg_box_d2(double h, double lx, double ly, double lz, int dx, int dy, int dz) {
-  const double ax = dx == 0 ? 0.0 : (dx < 0 ? lx + (double)(-dx - 1) * h : (h - lx) + (double)(dx - 1) * h);
-  const double ay = dy == 0 ? 0.0 : (dy < 0 ? ly + (double)(-dy - 1) * h : (h - ly) + (double)(dy - 1) * h);
-  const double az = dz == 0 ? 0.0 : (dz < 0 ? lz + (double)(-dz - 1) * h : (h - lz) + (double)(dz - 1) * h);
-  return ax * ax + ay * ay + az * az;
+// |d2_f32 - d2_exact| <= M for every candidate within r of the query: with e = 2^-23 (max|q| + 2r) bounding the
+// error of one f32 coordinate difference (rounding q to f32 + the subtraction; |difference| <= 3h < 2r),
+// sum(af^2) - sum(a^2) <= e (2 sqrt(3) r + 3 e), and the three roundings of the f32 sum add < 2^-22 r^2.
+__device__ __forceinline__ double nn_margin(double qx, double qy, double qz, double r, double r2) {
+  const double qmax = fmax(fmax(fabs(qx), fabs(qy)), fabs(qz));
+  const double e = (qmax + 2.0 * r) * (1.0 / 8388608.0);
+  return 4.0 * e * r + 4.0 * e * e + r2 * (1.0 / 2097152.0);
 }
 
-__device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int cz, double qx, double qy,
-                                             double qz, double r2, NNState& st) {
+__device__ __forceinline__ void nn_refresh(NNState& st, double M, double box_abs) {
+  st.thr = __double2float_ru(st.best + M);
+  st.thr_box = __double2float_ru(st.best + (st.best * 1e-6 + box_abs));
+}
+
+// f32 squared distance from the query (offset (lx,ly,lz) inside its own cell) to the box of the cell at
+// integer offset (dx,dy,dz); absolute error < 4e-6 h^2 (box_abs) + 1e-6 of the value
+__device__ __forceinline__ float hg_box_d2f(float h, float lx, float ly, float lz, int dx, int dy, int dz) {
+  const float ax = dx == 0 ? 0.0f : (dx < 0 ? lx + (float)(-dx - 1) * h : (h - lx) + (float)(dx - 1) * h);
+  const float ay = dy == 0 ? 0.0f : (dy < 0 ? ly + (float)(-dy - 1) * h : (h - ly) + (float)(dy - 1) * h);
+  const float az = dz == 0 ? 0.0f : (dz < 0 ? lz + (float)(-dz - 1) * h : (h - lz) + (float)(dz - 1) * h);
+  return fmaf(az, az, fmaf(ay, ay, ax * ax));
+}
+// the same for the 3^3 neighbourhood (|d| <= 1)
+__device__ __forceinline__ float hg_box_d2f_ring1(float h, float lx, float ly, float lz, int dx, int dy, int dz) {
+  const float ax = dx == 0 ? 0.0f : (dx < 0 ? lx : h - lx);
+  const float ay = dy == 0 ? 0.0f : (dy < 0 ? ly : h - ly);
+  const float az = dz == 0 ? 0.0f : (dz < 0 ? lz : h - lz);
+  return fmaf(az, az, fmaf(ay, ay, ax * ax));
+}
+
+struct NNQuery {
+  double x, y, z;     // exact (f64) query
+  float fx, fy, fz;   // rounded to f32
+  double M, box_abs;  // error bounds of the f32 candidate / box tests
+};
+
+__device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int cz, const NNQuery& q, double r2,
+                                             NNState& st) {
   const unsigned long long key = pack_key(cx, cy, cz);
   unsigned long long slot = mix64(key) & g.mask;
   unsigned s = 0, e = 0;
@@ -327,12 +362,15 @@ __device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int
   }
   for (unsigned j = s; j < e; ++j) {
     const float4 t = __ldg(g.xyzi + j);
-    const double ddx = (double)t.x - qx, ddy = (double)t.y - qy, ddz = (double)t.z - qz;
+    const float ax = t.x - q.fx, ay = t.y - q.fy, az = t.z - q.fz;
+    if (fmaf(az, az, fmaf(ay, ay, ax * ax)) > st.thr) continue;
+    const double ddx = (double)t.x - q.x, ddy = (double)t.y - q.y, ddz = (double)t.z - q.z;
     const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
     if (d2 < st.best || (d2 == st.best && d2 <= r2 && __float_as_uint(t.w) < st.bo)) {
       st.best = d2;
       st.bj = (int)j;
       st.bo = __float_as_uint(t.w);
+      nn_refresh(st, q.M, q.box_abs);
     }
   }
 }
@@ -435,6 +473,7 @@ __global__ void __launch_bounds__(NN_THREADS, 4)
   __shared__ double s_T[12];
   if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
   __syncthreads();
+  const double r = sqrt(r2);
   const unsigned l = lane_id();
   const unsigned grp = l / NN_GROUP, sub = l % NN_GROUP;
   const unsigned gmask = 0xFFu << (grp * NN_GROUP);
@@ -461,33 +500,44 @@ __global__ void __launch_bounds__(NN_THREADS, 4)
     }
     int cx, cy, cz;
     if (hg_cell(g, sx, sy, sz, cx, cy, cz) && (!near_filter || hg_near_target(g, cx, cy, cz))) {  // group-uniform
-      const double lx = sx - (double)cx * g.h, ly = sy - (double)cy * g.h, lz = sz - (double)cz * g.h;
-      const double hh = 0.5 * g.h;
+      NNQuery q;
+      q.x = sx; q.y = sy; q.z = sz;
+      q.fx = (float)sx; q.fy = (float)sy; q.fz = (float)sz;
+      q.M = nn_margin(sx, sy, sz, r, r2);
+      q.box_abs = 4e-6 * g.h * g.h;
+      nn_refresh(nn, q.M, q.box_abs);
+      const float hf = (float)g.h;
+      const float lx = (float)(sx - (double)cx * g.h), ly = (float)(sy - (double)cy * g.h),
+                  lz = (float)(sz - (double)cz * g.h);
+      const float hh = 0.5f * hf;
       const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
       {  // step 1: one octant cell per lane
         const int dx = (sub & 1) ? ox : 0, dy = (sub & 2) ? oy : 0, dz = (sub & 4) ? oz : 0;
-        if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) <= nn.best)  // (0 for the query's own cell)
-          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
+        if (hg_box_d2f_ring1(hf, lx, ly, lz, dx, dy, dz) <= nn.thr_box)  // (0 for the query's own cell)
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
       }
       nn_group_min(nn, gmask);
-      // step 2: the rest of ring 1
+      nn_refresh(nn, q.M, q.box_abs);
+      // step 2: the rest of ring 1 (cells in index order; the octant's 8 were done in step 1)
 #pragma unroll 1
-      for (int c = 1 + (int)sub; c < 27; c += NN_GROUP) {
-        const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
+      for (int c = (int)sub; c < 27; c += NN_GROUP) {
+        const int dz = c / 9 - 1, dy = (c - (dz + 1) * 9) / 3 - 1, dx = c - (dz + 1) * 9 - (dy + 1) * 3 - 1;
         if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
-        if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > nn.best) continue;
-        hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
+        if (hg_box_d2f_ring1(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
+        hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
       }
       nn_group_min(nn, gmask);
-      // after rings 0+1 everything closer than h + (distance of q to its cell's faces) has been seen
-      const double face = fmax(0.0, fmin(fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly)), fmin(lz, g.h - lz)));
-      const double reach1 = g.h + face;
-      if (!(nn.best <= reach1 * reach1)) {  // step 3: ring 2 (group-uniform branch)
+      // after rings 0+1 everything closer than h + (distance of q to its cell's faces) has been seen; the f32
+      // form of that radius is shrunk by more than its rounding error, so ring 2 is never skipped wrongly
+      const float face = fmaxf(0.0f, fminf(fminf(fminf(lx, hf - lx), fminf(ly, hf - ly)), fminf(lz, hf - lz)));
+      const float reach1 = (hf + face) * 0.99999f;
+      if (!(__double2float_ru(nn.best) <= __fmul_rd(reach1, reach1))) {  // step 3: ring 2 (group-uniform branch)
+        nn_refresh(nn, q.M, q.box_abs);
 #pragma unroll 1
         for (int c = 27 + (int)sub; c < 125; c += NN_GROUP) {
           const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
-          if (hg_box_d2(g.h, lx, ly, lz, dx, dy, dz) > nn.best) continue;
-          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, sx, sy, sz, r2, nn);
+          if (hg_box_d2f(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
         }
         nn_group_min(nn, gmask);
       }
@@ -621,6 +671,17 @@ __global__ void __launch_bounds__(ICP_THREADS)
   }
 }
 
+// correspondences as ORIGINAL target indices (t3d_icp_correspondences)
+__global__ void icp_corr_export_kernel(const __grid_constant__ HGrid g, const int* __restrict__ corr,
+                                       const double* __restrict__ corr_d2, long long n, int* __restrict__ out_idx,
+                                       double* __restrict__ out_d2) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = corr[i];
+  out_idx[i] = j < 0 ? -1 : (int)__float_as_uint(g.xyzi[j].w);
+  out_d2[i] = corr_d2[i];
+}
+
 }  // namespace
 
 // n_src / n_tgt are exact counts, or capacities when n_src_dev / n_tgt_dev point at the actual
@@ -629,7 +690,8 @@ __global__ void __launch_bounds__(ICP_THREADS)
 static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long long* n_src_dev, const float* tgt,
                      const float* tgt_nrm, int64_t n_tgt, const long long* n_tgt_dev, int min_points,
                      double max_corr, const double* T0, int max_iter, double rel_fitness,
-                     double rel_rmse, t3d_icp_result* res, int* skipped_h, cudaStream_t st) {
+                     double rel_rmse, t3d_icp_result* res, int* skipped_h, cudaStream_t st,
+                     int* out_idx = nullptr, double* out_d2 = nullptr, const double* T1 = nullptr) {
   T3D_REQUIRE(n_tgt < (1ll << 31) && n_src < (1ll << 40), "icp: cloud too large");
   unsigned long long hc = 1024;
   while (hc < 2ull * (unsigned long long)n_tgt) hc <<= 1;
@@ -724,6 +786,27 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
     T3D_CUDA(cudaMemcpyAsync(hflag, g.cursor, 8, cudaMemcpyDeviceToHost, st));
     return T3D_OK;
   };
+
+  if (out_idx) {  // t3d_icp_correspondences: one cold search at T0, optionally one warm search at T1
+    if ((rc = enqueue_all(0, true)) != T3D_OK) return rc;
+    icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
+    T3D_LAUNCH_CHECK();
+    T3D_CUDA(cudaStreamSynchronize(st));
+    if (T1) {
+      for (int i = 0; i < 16; ++i) hst->T[i] = T1[i];
+      hst->round = 1;
+      T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
+    }
+    icp_corr_export_kernel<<<(unsigned)((n_src + 255) / 256), 256, 0, st>>>(g, corr, corr_d2, (long long)n_src, out_idx, out_d2);
+    T3D_LAUNCH_CHECK();
+    T3D_CUDA(cudaStreamSynchronize(st));
+    if (hflag[1]) {
+      t3d_set_error("icp: target coordinates exceed +-2^19 * max_corr_dist");
+      return T3D_E_NUMERIC;
+    }
+    return T3D_OK;
+  }
 
   // rounds needed: at most max_iter + 1.  Enqueue speculatively (finished rounds are no-op
   // launches), read the state back, continue only if the registration is still running.
@@ -834,6 +917,20 @@ extern "C" int t3d_icp_point_to_plane(t3d_ctx* ctx, const float* src, int64_t n_
   cudaStream_t st = as_stream(stream);
   return icp_fused(ctx, src, n_src, nullptr, tgt, tgt_nrm, n_tgt, nullptr, 0, max_corr_dist, res->T, max_iter,
                    rel_fitness, rel_rmse, res, nullptr, st);
+}
+
+extern "C" int t3d_icp_correspondences(t3d_ctx* ctx, const float* src, int64_t n_src, const float* tgt,
+                                       const float* tgt_nrm, int64_t n_tgt, double max_corr_dist,
+                                       const double* T0_h, const double* T1_h, int32_t* out_idx, double* out_d2,
+                                       t3d_stream stream) {
+  T3D_REQUIRE(ctx && src && tgt && tgt_nrm && T0_h && out_idx && out_d2 && n_src > 0 && n_tgt > 0,
+              "t3d_icp_correspondences: null argument");
+  T3D_ON_DEVICE(ctx->device);
+  T3D_REQUIRE(max_corr_dist > 0.0, "t3d_icp_correspondences: bad parameters");
+  t3d_icp_result res;
+  memset(&res, 0, sizeof(res));
+  return icp_fused(ctx, src, n_src, nullptr, tgt, tgt_nrm, n_tgt, nullptr, 0, max_corr_dist, T0_h, 0, 0.0, 0.0, &res,
+                   nullptr, as_stream(stream), out_idx, out_d2, T1_h);
 }
 
 extern "C" int t3d_icp_point_to_plane_dev(t3d_ctx* ctx, const float* src, int64_t src_capacity,

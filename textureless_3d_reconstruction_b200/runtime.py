@@ -440,6 +440,22 @@ class Context:
                         res.iterations, bool(res.converged), int(res.correspondences))
         return out, bool(skipped.value)
 
+    def icp_correspondences(self, src, tgt, tgt_nrm, max_corr_dist, T0, T1=None):
+        """The registration's correspondence search on its own: (original target index or -1, squared distance
+        f64) per source point at pose T0; with T1, a second search at T1 seeded with the first one's answers."""
+        torch = _torch()
+        for t in (src, tgt, tgt_nrm):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        n = src.shape[0]
+        idx = torch.empty(max(n, 1), dtype=torch.int32, device=src.device)
+        d2 = torch.empty(max(n, 1), dtype=torch.float64, device=src.device)
+        T0h = np.ascontiguousarray(T0, np.float64).reshape(16)
+        T1h = None if T1 is None else np.ascontiguousarray(T1, np.float64).reshape(16)
+        check(self.lib.t3d_icp_correspondences(self.handle, _ptr(src), n, _ptr(tgt), _ptr(tgt_nrm), tgt.shape[0],
+                                               float(max_corr_dist), _np_ptr(T0h), _np_ptr(T1h), _ptr(idx), _ptr(d2),
+                                               _stream()))
+        return idx[:n], d2[:n]
+
     def icp_linearize(self, src, tgt, tgt_nrm, max_corr_dist, T):
         """One linearisation: returns (acc27, sum_d2, count) as host values."""
         Th = np.ascontiguousarray(T, np.float64).reshape(16)
