@@ -9,7 +9,7 @@
 // with warp shuffles, then per-CTA partials are summed by one CTA in a fixed
 // order (deterministic).  No tensor cores: this is a gather + reduction.
 // t3d_icp_point_to_plane keeps the whole registration on the device
-// (icp_nn_kernel / icp_acc_kernel below); t3d_icp_linearize keeps the
+// (icp_nn_kernel below); t3d_icp_linearize keeps the
 // one-linearisation-per-call form for the multi-GPU all-reduce path.
 #include <math.h>
 
@@ -146,10 +146,14 @@ int linearize(t3d_ctx* ctx, const GridDev& g, const float* src, long long n_src,
 
 namespace {
 
+struct __align__(16) HSlot {  // one 16-byte load answers a probe: the cell's key and its point range
+  unsigned long long key1;    // pack_key + 1; 0 = empty (the table is cleared with one memset)
+  unsigned start;             // first sorted position of the cell
+  unsigned count;             // points in the cell
+};
+
 struct HGrid {            // cells of size h keyed by floor(p / h) (biased 21-bit pack_key)
-  unsigned long long* keys;
-  unsigned* count;        // points in the cell
-  unsigned* start;        // first sorted position of the cell
+  HSlot* slots;
   unsigned* fill;         // scatter cursor
   unsigned long long* coarse_keys;  // set of occupied coarse cells (input of the dilation)
   unsigned long long* near_keys;  // set of coarse cells (2h = max_corr) with a target within one coarse
@@ -188,15 +192,15 @@ __global__ void hg_count_kernel(const float* __restrict__ tgt, const __grid_cons
        i += (long long)gridDim.x * blockDim.x) {
     int cx, cy, cz;
     if (!hg_cell(g, tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2], cx, cy, cz)) { g.cursor[1] = 1; continue; }
-    const unsigned long long key = pack_key(cx, cy, cz);
+    const unsigned long long key = pack_key(cx, cy, cz), key1 = key + 1ull;
     unsigned long long slot = mix64(key) & g.mask;
     while (true) {
-      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(g.keys + slot));
-      if (k == T3D_KEY_EMPTY) k = atomicCAS(g.keys + slot, T3D_KEY_EMPTY, key);
-      if (k == T3D_KEY_EMPTY || k == key) break;
+      unsigned long long k = ld_volatile_u64(reinterpret_cast<const uint64_t*>(&g.slots[slot].key1));
+      if (k == 0ull) k = atomicCAS(&g.slots[slot].key1, 0ull, key1);
+      if (k == 0ull || k == key1) break;
       slot = (slot + 1) & g.mask;
     }
-    atomicAdd(g.count + slot, 1u);
+    atomicAdd(&g.slots[slot].count, 1u);
   }
 }
 
@@ -209,7 +213,7 @@ __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g, int with_coarse
   const unsigned lane = lane_id();
   for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s <= g.mask;
        s += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned c = g.count[s];
+    const unsigned c = g.slots[s].count;
     unsigned incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -222,12 +226,12 @@ __global__ void hg_alloc_kernel(const __grid_constant__ HGrid g, int with_coarse
     if (lane == 31) base = atomicAdd(g.cursor, total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (!c) continue;
-    g.start[s] = base + (incl - c);
+    g.slots[s].start = base + (incl - c);
     if (!with_coarse) continue;
     // note this fine cell's coarse cell (2h); hg_dilate_kernel then marks the 27 coarse cells around
     // every occupied coarse cell — one dilation per coarse cell instead of one per fine cell
     int fx, fy, fz;
-    unpack_key(g.keys[s], fx, fy, fz);
+    unpack_key(g.slots[s].key1 - 1ull, fx, fy, fz);
     const unsigned long long key = pack_key(fx >> 1, fy >> 1, fz >> 1);
     unsigned long long slot = mix64(key) & g.mask;
     while (true) {
@@ -288,8 +292,8 @@ __global__ void hg_scatter_kernel(const float* __restrict__ tgt, const float* __
     if (!hg_cell(g, x, y, z, cx, cy, cz)) continue;
     const unsigned long long key = pack_key(cx, cy, cz);
     unsigned long long slot = mix64(key) & g.mask;
-    while (g.keys[slot] != key) slot = (slot + 1) & g.mask;
-    const unsigned pos = g.start[slot] + atomicAdd(g.fill + slot, 1u);
+    while (g.slots[slot].key1 != key + 1ull) slot = (slot + 1) & g.mask;
+    const unsigned pos = g.slots[slot].start + atomicAdd(g.fill + slot, 1u);
     g.xyzi[pos] = make_float4(x, y, z, __uint_as_float((unsigned)i));
     g.nrm[3ll * pos] = tgt_nrm[3 * i]; g.nrm[3ll * pos + 1] = tgt_nrm[3 * i + 1]; g.nrm[3ll * pos + 2] = tgt_nrm[3 * i + 2];
   }
@@ -349,36 +353,66 @@ struct NNQuery {
   double M, box_abs;  // error bounds of the f32 candidate / box tests
 };
 
-__device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int cz, const NNQuery& q, double r2,
-                                             NNState& st) {
-  const unsigned long long key = pack_key(cx, cy, cz);
-  unsigned long long slot = mix64(key) & g.mask;
-  unsigned s = 0, e = 0;
-  while (true) {
-    const unsigned long long k = __ldg(g.keys + slot);
-    if (k == key) { s = __ldg(g.start + slot); e = s + __ldg(g.count + slot); break; }
-    if (k == T3D_KEY_EMPTY) break;
-    slot = (slot + 1) & g.mask;
+// one candidate (already loaded): f32 rejection, f64 decision
+__device__ __forceinline__ void nn_candidate_v(const float4 t, unsigned j, const NNQuery& q, double r2, NNState& st) {
+  const float ax = t.x - q.fx, ay = t.y - q.fy, az = t.z - q.fz;
+  if (fmaf(az, az, fmaf(ay, ay, ax * ax)) > st.thr) return;
+  const double ddx = (double)t.x - q.x, ddy = (double)t.y - q.y, ddz = (double)t.z - q.z;
+  const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+  if (d2 < st.best || (d2 == st.best && d2 <= r2 && __float_as_uint(t.w) < st.bo)) {
+    st.best = d2;
+    st.bj = (int)j;
+    st.bo = __float_as_uint(t.w);
+    nn_refresh(st, q.M, q.box_abs);
   }
-  for (unsigned j = s; j < e; ++j) {
-    const float4 t = __ldg(g.xyzi + j);
-    const float ax = t.x - q.fx, ay = t.y - q.fy, az = t.z - q.fz;
-    if (fmaf(az, az, fmaf(ay, ay, ax * ax)) > st.thr) continue;
-    const double ddx = (double)t.x - q.x, ddy = (double)t.y - q.y, ddz = (double)t.z - q.z;
-    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    if (d2 < st.best || (d2 == st.best && d2 <= r2 && __float_as_uint(t.w) < st.bo)) {
-      st.best = d2;
-      st.bj = (int)j;
-      st.bo = __float_as_uint(t.w);
-      nn_refresh(st, q.M, q.box_abs);
-    }
+}
+__device__ __forceinline__ void nn_candidate(const HGrid& g, unsigned j, const NNQuery& q, double r2, NNState& st) {
+  nn_candidate_v(__ldg(g.xyzi + j), j, q, r2, st);
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ uint4 hg_load_slot(const HGrid& g, unsigned long long slot) {
+  return __ldg(reinterpret_cast<const uint4*>(g.slots + slot));
+}
+
+// Point range [s, e) of the cell with key `key`, starting from its home slot whose contents `sl` were loaded
+// earlier (the caller issues that load as soon as the cell is known, long before it needs the answer).
+__device__ __forceinline__ void hg_cell_range(const HGrid& g, unsigned long long key, unsigned long long slot, uint4 sl,
+                                              unsigned& s, unsigned& e) {
+  const unsigned k1lo = (unsigned)(key + 1ull), k1hi = (unsigned)((key + 1ull) >> 32);
+  s = 0; e = 0;
+  while (true) {
+    if (sl.x == k1lo && sl.y == k1hi) { s = sl.z; e = s + sl.w; break; }
+    if ((sl.x | sl.y) == 0u) break;
+    slot = (slot + 1) & g.mask;
+    sl = hg_load_slot(g, slot);
   }
 }
 
-// (d2, original index) arg-min across the 8 lanes of a query group
+__device__ __forceinline__ void hg_scan_cell_from(const HGrid& g, unsigned long long key, unsigned long long slot,
+                                                  uint4 sl, const NNQuery& q, double r2, NNState& st) {
+  unsigned s, e;
+  hg_cell_range(g, key, slot, sl, s, e);
+  for (unsigned j = s; j < e; ++j) nn_candidate(g, j, q, r2, st);
+}
+
+__device__ __forceinline__ void hg_scan_cell(const HGrid& g, int cx, int cy, int cz, const NNQuery& q, double r2,
+                                             NNState& st) {
+  const unsigned long long key = pack_key(cx, cy, cz);
+  const unsigned long long slot = mix64(key) & g.mask;
+  hg_scan_cell_from(g, key, slot, hg_load_slot(g, slot), q, r2, st);
+}
+
+// (d2, original index) arg-min across the G lanes of a query group
+template <int G>
 __device__ __forceinline__ void nn_group_min(NNState& st, unsigned gmask) {
 #pragma unroll
-  for (int d = 4; d > 0; d >>= 1) {
+  for (int d = G / 2; d > 0; d >>= 1) {
     const double ob = __shfl_xor_sync(gmask, st.best, d);
     const int oj = __shfl_xor_sync(gmask, st.bj, d);
     const unsigned oo = __shfl_xor_sync(gmask, st.bo, d);
@@ -439,116 +473,93 @@ struct IcpState {       // device-resident registration state (also the D2H resu
   int iterations, converged, done, round;
   unsigned ticket;
   int skipped;          // device-count mode: a cloud was smaller than min_points
+  unsigned long long dbg[8];  // T3D_ICP_TIMING: globaltimer stamps of the last linearisation (ns)
 };
 
-// One linearisation = two launches, both of which return at once when the
-// registration has already finished (st->done), so the host can enqueue several
-// rounds without a round trip per iteration:
-//   icp_nn_kernel   correspondences only — small register footprint, many resident
-//                   warps to hide the latency of the hash probes and candidate loads;
-//   icp_acc_kernel  J^T J / J^T r accumulation from the stored correspondences; the
-//                   last CTA to finish sums the per-CTA partials in blockIdx order
-//                   (deterministic), checks convergence and solves the 6x6 system.
-constexpr int NN_THREADS = 256;
-constexpr int NN_GROUP = 8;  // lanes per query
+// fixed pairwise tree over the per-warp rows of s (NW a power of two)
+template <int NW>
+__device__ __forceinline__ double tree_sum(const double (*s)[NACC], int k) {
+  double t[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) t[i] = s[i][k];
+#pragma unroll
+  for (int h = 1; h < NW; h <<= 1)
+#pragma unroll
+    for (int i = 0; i + h < NW; i += 2 * h) t[i] += t[i + h];
+  return t[0];
+}
 
-// Exact nearest neighbour, EIGHT lanes per query (the clouds of one frame hold ~1e5 queries:
-// one thread per query leaves the GPU short of warps and gives every warp a long dependent
-// chain of hash probes).  Step 1: the 8 lanes probe the 8 cells of the query's octant (its own
-// cell and the neighbours on the side the query sits in) at once — with h ~ 2-3 surface
-// samples these almost always contain the answer.  Step 2: the other 19 cells of ring 1 are
-// dealt round-robin; a cell is probed only if its box is closer than the best so far.
-// Step 3 (rare): ring 2 the same way, only if something closer could still hide there.
-// Between steps the group takes an arg-min over (d2, original index) with 3 shuffles.
-__global__ void __launch_bounds__(NN_THREADS, 4)
-    icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
-                  const long long* n_src_dev, double r2, const IcpState* st, int* __restrict__ corr,
-                  double* __restrict__ corr_d2, int near_filter) {
-  if (*reinterpret_cast<const volatile int*>(&st->done)) return;
-  // from the second linearisation on, corr[] holds the previous round's answer for this registration: it
-  // seeds the search as the incumbent (exact: any valid candidate may), and because the pose moves little
-  // between rounds the seed is almost always the answer already, so nearly every cell fails the box test
-  const bool warm = *reinterpret_cast<const volatile int*>(&st->round) > 0;
-  if (n_src_dev) { const long long v = *n_src_dev; n_src = v < n_src ? v : n_src; }
-  __shared__ double s_T[12];
-  if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
+// The last CTA of a linearisation finishes the round: fixed-order sum of the per-CTA partials (warp w takes
+// every NW-th row with 8 independent accumulators — deterministic), convergence bookkeeping as R8, the 6x6
+// solve by one warp and the pose update.  Called by all NW warps of that CTA.
+template <int NW>
+__device__ __forceinline__ void icp_finish_round(IcpState* st, const double* partial, unsigned nb, long long n_src,
+                                                 const HGrid& g, int min_points, int max_iter, double rel_fitness,
+                                                 double rel_rmse, double (*s)[NACC]) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  {
+    const int k = l;
+    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (k < NACC) {
+      unsigned b = w;
+      for (; b + 7 * NW < nb; b += 8 * NW) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          a8[u] += *reinterpret_cast<const volatile double*>(&partial[(long long)(b + NW * u) * NACC + k]);
+      }
+      for (int u = 0; b < nb; b += NW, ++u)
+        a8[u & 7] += *reinterpret_cast<const volatile double*>(&partial[(long long)b * NACC + k]);
+      s[w][k] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+    }
+  }
   __syncthreads();
-  const double r = sqrt(r2);
-  const unsigned l = lane_id();
-  const unsigned grp = l / NN_GROUP, sub = l % NN_GROUP;
-  const unsigned gmask = 0xFFu << (grp * NN_GROUP);
-  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  constexpr int QPW = 32 / NN_GROUP;  // queries per warp
-  for (long long qb = warp_global * QPW; qb < n_src; qb += total_warps * QPW) {
-    const long long i = qb + grp;
-    if (i >= n_src) continue;  // group-uniform
-    const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
-    const double sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
-    const double sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
-    const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
-    NNState nn;
-    nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
-    if (warm) {
-      const int pj = corr[i];
-      if (pj >= 0) {
-        const float4 t = __ldg(g.xyzi + pj);
-        const double ddx = (double)t.x - sx, ddy = (double)t.y - sy, ddz = (double)t.z - sz;
-        const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-        if (d2 <= r2) { nn.best = d2; nn.bj = pj; nn.bo = __float_as_uint(t.w); }
-      }
+  if (threadIdx.x < NACC) st->acc[threadIdx.x] = tree_sum<NW>(s, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) st->dbg[3] = gtime();
+  if (w == 0) {  // convergence bookkeeping (uniform across the warp) + warp-parallel 6x6 solve
+    const int round = st->round;
+    const double cnt = st->acc[28];
+    const double f2 = cnt / (double)n_src;
+    const double e2 = cnt > 0.0 ? sqrt(st->acc[27] / cnt) : 0.0;
+    bool done = false;
+    int converged = 0;
+    if (round > 0 && fabs(st->fitness - f2) < rel_fitness && fabs(st->rmse - e2) < rel_rmse) {
+      converged = 1;
+      done = true;
     }
-    int cx, cy, cz;
-    if (hg_cell(g, sx, sy, sz, cx, cy, cz) && (!near_filter || hg_near_target(g, cx, cy, cz))) {  // group-uniform
-      NNQuery q;
-      q.x = sx; q.y = sy; q.z = sz;
-      q.fx = (float)sx; q.fy = (float)sy; q.fz = (float)sz;
-      q.M = nn_margin(sx, sy, sz, r, r2);
-      q.box_abs = 4e-6 * g.h * g.h;
-      nn_refresh(nn, q.M, q.box_abs);
-      const float hf = (float)g.h;
-      const float lx = (float)(sx - (double)cx * g.h), ly = (float)(sy - (double)cy * g.h),
-                  lz = (float)(sz - (double)cz * g.h);
-      const float hh = 0.5f * hf;
-      const int ox = lx < hh ? -1 : 1, oy = ly < hh ? -1 : 1, oz = lz < hh ? -1 : 1;
-      {  // step 1: one octant cell per lane
-        const int dx = (sub & 1) ? ox : 0, dy = (sub & 2) ? oy : 0, dz = (sub & 4) ? oz : 0;
-        if (hg_box_d2f_ring1(hf, lx, ly, lz, dx, dy, dz) <= nn.thr_box)  // (0 for the query's own cell)
-          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
+    if (!done && round >= max_iter) done = true;
+    // device-count mode: clouds below min_points are not registered (pose = initial guess)
+    const bool skipped = min_points > 0 && (n_src < min_points || hg_n(g) < min_points);
+    if (skipped) done = true;
+    double x[6] = {0, 0, 0, 0, 0, 0};
+    bool solved = false;
+    if (!done) solved = warp_solve6(st->acc, x, l);
+    __syncwarp();
+    if (l == 0) {
+      st->dbg[4] = gtime();
+      if (skipped) st->skipped = 1;
+      if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
+      if (converged) st->converged = 1;
+      st->fitness = f2;
+      st->rmse = e2;
+      if (!done && solved) {  // ill-posed -> identity update (R8)
+        double U[16], Tn[16], Tc[16];
+        for (int i = 0; i < 16; ++i) Tc[i] = st->T[i];
+        vec6_to_mat4(x, U);
+        mat4_mul(U, Tc, Tn);
+        for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
       }
-      nn_group_min(nn, gmask);
-      nn_refresh(nn, q.M, q.box_abs);
-      // step 2: the rest of ring 1 (cells in index order; the octant's 8 were done in step 1)
-#pragma unroll 1
-      for (int c = (int)sub; c < 27; c += NN_GROUP) {
-        const int dz = c / 9 - 1, dy = (c - (dz + 1) * 9) / 3 - 1, dx = c - (dz + 1) * 9 - (dy + 1) * 3 - 1;
-        if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
-        if (hg_box_d2f_ring1(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
-        hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
-      }
-      nn_group_min(nn, gmask);
-      // after rings 0+1 everything closer than h + (distance of q to its cell's faces) has been seen; the f32
-      // form of that radius is shrunk by more than its rounding error, so ring 2 is never skipped wrongly
-      const float face = fmaxf(0.0f, fminf(fminf(fminf(lx, hf - lx), fminf(ly, hf - ly)), fminf(lz, hf - lz)));
-      const float reach1 = (hf + face) * 0.99999f;
-      if (!(__double2float_ru(nn.best) <= __fmul_rd(reach1, reach1))) {  // step 3: ring 2 (group-uniform branch)
-        nn_refresh(nn, q.M, q.box_abs);
-#pragma unroll 1
-        for (int c = 27 + (int)sub; c < 125; c += NN_GROUP) {
-          const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
-          if (hg_box_d2f(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
-          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
-        }
-        nn_group_min(nn, gmask);
-      }
-    }
-    if (sub == 0) {
-      corr[i] = nn.bj;
-      corr_d2[i] = nn.best;
+      st->round = round + 1;
+      st->ticket = 0;
+      st->dbg[5] = gtime();
+      __threadfence();
+      st->done = done ? 1 : 0;
     }
   }
 }
 
+// The linearisation as its own launch (after a search with fewer than 8 lanes per query): one thread per
+// correspondence accumulates the 29 sums, warp shuffles + a fixed tree per CTA, the last CTA finishes the round.
 __global__ void __launch_bounds__(ICP_THREADS)
     icp_acc_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
                    const long long* n_src_dev, int min_points, int max_iter, double rel_fitness, double rel_rmse,
@@ -599,76 +610,214 @@ __global__ void __launch_bounds__(ICP_THREADS)
   if (l == 0)
     for (int k = 0; k < NACC; ++k) s[w][k] = acc[k];
   __syncthreads();
-  if (threadIdx.x < NACC) {
-    double t = 0.0;
-    for (int ww = 0; ww < ICP_THREADS / 32; ++ww) t += s[ww][threadIdx.x];
-    partial[(long long)blockIdx.x * NACC + threadIdx.x] = t;
-  }
-  // last CTA to arrive finishes the round
+  if (threadIdx.x < NACC) partial[(long long)blockIdx.x * NACC + threadIdx.x] = tree_sum<ICP_THREADS / 32>(s, threadIdx.x);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  {  // fixed-order final sum: warp w takes every 4th partial with 8 independent accumulators
-    const int k = l;
-    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (k < NACC) {
-      const unsigned nb = gridDim.x;
-      unsigned b = w;
-      for (; b + 28 < nb; b += 32) {
+  icp_finish_round<ICP_THREADS / 32>(st, partial, gridDim.x, n_src, g, min_points, max_iter, rel_fitness, rel_rmse, s);
+}
+
+// One linearisation = ONE launch that returns at once when the registration has already
+// finished (st->done), so the host can enqueue several rounds without a round trip per
+// iteration: icp_nn_kernel finds the correspondences and, fused into the same pass, the 8
+// lanes of each query group share out the 29 sums of J^T J / J^T r; the last CTA to finish
+// adds the per-CTA partials in blockIdx order (deterministic), checks convergence and
+// solves the 6x6 system (icp_finish_round).
+constexpr int NN_THREADS = 256;
+constexpr int NN_GROUP = 8;  // lanes per query
+
+// Exact nearest neighbour, EIGHT lanes per query (the clouds of one frame hold ~1e5 queries:
+// one thread per query leaves the GPU short of warps and gives every warp a long dependent
+// chain of hash probes).  Step 1: the 8 lanes probe the 8 cells of the query's octant (its own
+// cell and the neighbours on the side the query sits in) at once — with h ~ 2-3 surface
+// samples these almost always contain the answer.  Step 2: the other 19 cells of ring 1 are
+// dealt round-robin; a cell is probed only if its box is closer than the best so far.
+// Step 3 (rare): ring 2 the same way, only if something closer could still hide there.
+// Between steps the group takes an arg-min over (d2, original index) with 3 shuffles.
+__global__ void __launch_bounds__(NN_THREADS, 4)
+    icp_nn_kernel(const __grid_constant__ HGrid g, const float* __restrict__ src, long long n_src,
+                  const long long* n_src_dev, double r2, IcpState* st, int* __restrict__ corr,
+                  double* __restrict__ corr_d2, int near_filter, int fuse, int min_points, int max_iter,
+                  double rel_fitness, double rel_rmse, double* partial /* gridDim.x * NACC */) {
+  if (*reinterpret_cast<const volatile int*>(&st->done)) return;
+  // from the second linearisation on, corr[] holds the previous round's answer for this registration: it
+  // seeds the search as the incumbent (exact: any valid candidate may), and because the pose moves little
+  // between rounds the seed is almost always the answer already, so nearly every cell fails the box test
+  const bool warm = *reinterpret_cast<const volatile int*>(&st->round) > 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[0] = gtime();
+  if (n_src_dev) { const long long v = *n_src_dev; n_src = v < n_src ? v : n_src; }
+  __shared__ double s_T[12];
+  if (threadIdx.x < 12) s_T[threadIdx.x] = *reinterpret_cast<const volatile double*>(&st->T[threadIdx.x]);
+  __syncthreads();
+  const double r = sqrt(r2);
+  const unsigned l = lane_id();
+  const unsigned grp = l / NN_GROUP, sub = l % NN_GROUP;
+  const unsigned gmask = 0xFFu << (grp * NN_GROUP);
+  // Linearisation fused into the search (fuse != 0): every lane of a query group holds J0..J5 (computed from the
+  // same broadcast loads), lane `sub` owns ONE of the group's 8 values {J0..J5, r, d2} and accumulates its products
+  // with the six J's — lanes 0..5 the rows of J^T J, lane 6 J^T r, lane 7 sum d2 and the count: no shuffles.
+  double accl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int QPW = 32 / NN_GROUP;  // queries per warp
+  for (long long qb = warp_global * QPW; qb < n_src; qb += total_warps * QPW) {
+    const long long i = qb + grp;
+    if (i >= n_src) continue;  // group-uniform
+    // every load that does not depend on a decision is issued up front: the point, last round's answer and the
+    // target it names, and the home slots of this lane's octant cells — two dependent round trips to memory
+    // before the candidates instead of five
+    const int pj = warm ? corr[i] : -1;
+    const double px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+    float4 seed = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pj >= 0) seed = __ldg(g.xyzi + pj);
+    const double sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+    const double sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+    const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
+    int cx, cy, cz;
+    const bool in_grid = hg_cell(g, sx, sy, sz, cx, cy, cz) && (!(near_filter & 1) || hg_near_target(g, cx, cy, cz));  // group-uniform
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    int ox = 1, oy = 1, oz = 1;
+    const float hf = (float)g.h;
+    unsigned long long okey = 0, oslot = 0;  // this lane's cell of the query's octant: cell `sub`
+    uint4 osl = make_uint4(0u, 0u, 0u, 0u);
+    if (in_grid) {
+      lx = (float)(sx - (double)cx * g.h); ly = (float)(sy - (double)cy * g.h); lz = (float)(sz - (double)cz * g.h);
+      const float hh = 0.5f * hf;
+      ox = lx < hh ? -1 : 1; oy = ly < hh ? -1 : 1; oz = lz < hh ? -1 : 1;
+      okey = pack_key(cx + ((sub & 1) ? ox : 0), cy + ((sub & 2) ? oy : 0), cz + ((sub & 4) ? oz : 0));
+      oslot = mix64(okey) & g.mask;
+      osl = hg_load_slot(g, oslot);
+    }
+    NNState nn;
+    nn.best = r2; nn.bj = -1; nn.bo = 0xFFFFFFFFu;
+    if (pj >= 0) {
+      const double ddx = (double)seed.x - sx, ddy = (double)seed.y - sy, ddz = (double)seed.z - sz;
+      const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+      if (d2 <= r2) { nn.best = d2; nn.bj = pj; nn.bo = __float_as_uint(seed.w); }
+    }
+    if (in_grid) {
+      NNQuery q;
+      q.x = sx; q.y = sy; q.z = sz;
+      q.fx = (float)sx; q.fy = (float)sy; q.fz = (float)sz;
+      q.M = nn_margin(sx, sy, sz, r, r2);
+      q.box_abs = 4e-6 * g.h * g.h;
+      nn_refresh(nn, q.M, q.box_abs);
+      {  // step 1: the 8 cells of the octant.  Lane t resolved cell t's range and box distance; the GROUP then
+         // visits the cells that can still hold a winner, one candidate per lane (a cell holds about as many
+         // points as the group has lanes).
+        unsigned cs, ce;
+        hg_cell_range(g, okey, oslot, osl, cs, ce);
+        const float bd = hg_box_d2f_ring1(hf, lx, ly, lz, (sub & 1) ? ox : 0, (sub & 2) ? oy : 0, (sub & 4) ? oz : 0);
+        unsigned pend = (__ballot_sync(gmask, ce > cs && bd <= nn.thr_box) >> (grp * NN_GROUP)) & 0xFFu;
+        // The cells that pass the box test against the incumbent at this point (the seed, from the second round on)
+        // are visited two per trip — both candidate loads in flight together — with private incumbents per lane
+        // and ONE arg-min at the end: a visit costs a memory round trip, an arg-min three dependent shuffle rounds.
+        while (pend) {  // group-uniform
+          const int t0 = __ffs(pend) - 1;
+          pend &= pend - 1u;
+          const int t1 = pend ? __ffs(pend) - 1 : t0;
+          const bool two = pend != 0u;
+          pend &= pend - 1u;
+          const int f0 = (int)(grp * NN_GROUP) + t0, f1 = (int)(grp * NN_GROUP) + t1;
+          const unsigned s0 = __shfl_sync(gmask, cs, f0), e0 = __shfl_sync(gmask, ce, f0);
+          const unsigned s1 = __shfl_sync(gmask, cs, f1), e1 = two ? __shfl_sync(gmask, ce, f1) : s1;
+          const bool va = s0 + sub < e0, vb = s1 + sub < e1;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (va) a = __ldg(g.xyzi + s0 + sub);
+          if (vb) b = __ldg(g.xyzi + s1 + sub);
+          if (va) nn_candidate_v(a, s0 + sub, q, r2, nn);
+          if (vb) nn_candidate_v(b, s1 + sub, q, r2, nn);
+          for (unsigned j0 = s0 + NN_GROUP; j0 < e0; j0 += NN_GROUP)  // cells with more points than lanes (rare)
+            if (j0 + sub < e0) nn_candidate(g, j0 + sub, q, r2, nn);
+          for (unsigned j0 = s1 + NN_GROUP; j0 < e1; j0 += NN_GROUP)
+            if (j0 + sub < e1) nn_candidate(g, j0 + sub, q, r2, nn);
+        }
+        nn_group_min<NN_GROUP>(nn, gmask);
+        nn_refresh(nn, q.M, q.box_abs);
+      }
+      // step 2: the rest of ring 1 (cells in index order; the octant's 8 were done in step 1).  Every one of those
+      // 19 cells lies beyond the FAR face of the query's cell on at least one axis, i.e. at least
+      // min_axis(max(l, h - l)) >= h / 2 away: with h ~ 2-3 surface samples the incumbent is almost always
+      // closer than that, and the whole step (and its arg-min) is skipped — group-uniform.
+      const float far_face = fminf(fminf(fmaxf(lx, hf - lx), fmaxf(ly, hf - ly)), fmaxf(lz, hf - lz));
+      if (far_face * far_face <= nn.thr_box) {
+#pragma unroll 1
+        for (int c = (int)sub; c < 27; c += NN_GROUP) {
+          const int dz = c / 9 - 1, dy = (c - (dz + 1) * 9) / 3 - 1, dx = c - (dz + 1) * 9 - (dy + 1) * 3 - 1;
+          if ((dx == 0 || dx == ox) && (dy == 0 || dy == oy) && (dz == 0 || dz == oz)) continue;  // octant: done
+          if (hg_box_d2f_ring1(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
+        }
+        nn_group_min<NN_GROUP>(nn, gmask);
+      }
+      // after rings 0+1 everything closer than h + (distance of q to its cell's faces) has been seen; the f32
+      // form of that radius is shrunk by more than its rounding error, so ring 2 is never skipped wrongly
+      const float face = fmaxf(0.0f, fminf(fminf(fminf(lx, hf - lx), fminf(ly, hf - ly)), fminf(lz, hf - lz)));
+      const float reach1 = (hf + face) * 0.99999f;
+      if (!(near_filter & 2) && !(__double2float_ru(nn.best) <= __fmul_rd(reach1, reach1))) {  // step 3: ring 2 (group-uniform branch)
+        nn_refresh(nn, q.M, q.box_abs);
+#pragma unroll 1
+        for (int c = 27 + (int)sub; c < 125; c += NN_GROUP) {
+          const int dx = c_ofs[c][0], dy = c_ofs[c][1], dz = c_ofs[c][2];
+          if (hg_box_d2f(hf, lx, ly, lz, dx, dy, dz) > nn.thr_box) continue;
+          hg_scan_cell(g, cx + dx, cy + dy, cz + dz, q, r2, nn);
+        }
+        nn_group_min<NN_GROUP>(nn, gmask);
+      }
+    }
+    if (sub == 0) {
+      corr[i] = nn.bj;
+      corr_d2[i] = nn.best;
+    }
+    if (fuse && nn.bj >= 0) {  // group-uniform
+      const float4 tp = __ldg(g.xyzi + nn.bj);
+      const double tx = tp.x, ty = tp.y, tz = tp.z;
+      const double nx = __ldg(g.nrm + 3ll * nn.bj), ny = __ldg(g.nrm + 3ll * nn.bj + 1), nz = __ldg(g.nrm + 3ll * nn.bj + 2);
+      const double res = (sx - tx) * nx + (sy - ty) * ny + (sz - tz) * nz;
+      const double j0 = sy * nz - sz * ny, j1 = sz * nx - sx * nz, j2 = sx * ny - sy * nx;
+      if (sub < 7) {
+        const double v = sub == 0 ? j0 : sub == 1 ? j1 : sub == 2 ? j2 : sub == 3 ? nx : sub == 4 ? ny : sub == 5 ? nz : res;
+        accl[0] += j0 * v; accl[1] += j1 * v; accl[2] += j2 * v;
+        accl[3] += nx * v; accl[4] += ny * v; accl[5] += nz * v;
+      } else {
+        accl[0] += nn.best;
+        accl[1] += 1.0;
+      }
+    }
+  }
+  if (!fuse) return;
+  const unsigned long long t_loop = gtime();
+  // warp: the four groups' sums; CTA: the eight warps' in a fixed tree; grid: the last CTA
+  __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          a8[u] += *reinterpret_cast<volatile double*>(&partial[(long long)(b + 4 * u) * NACC + k]);
-      }
-      for (int u = 0; b < nb; b += 4, ++u)
-        a8[u & 7] += *reinterpret_cast<volatile double*>(&partial[(long long)b * NACC + k]);
-      s[w][k] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+  for (int a = 0; a < 6; ++a) {
+    accl[a] += __shfl_xor_sync(0xffffffffu, accl[a], 8);
+    accl[a] += __shfl_xor_sync(0xffffffffu, accl[a], 16);
+  }
+  __shared__ double s_acc[NN_THREADS / 32][NACC];
+  __shared__ unsigned s_last;
+  const int w = threadIdx.x >> 5;
+  if (grp == 0) {  // lane `sub` holds row `sub` of the 7x6 product table [J;r] J^T: keep the packed upper triangle
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      if (sub < 6 && a >= (int)sub) s_acc[w][(int)sub * 6 - (int)sub * ((int)sub - 1) / 2 + (a - (int)sub)] = accl[a];
+      if (sub == 6) s_acc[w][21 + a] = accl[a];
     }
+    if (sub == 7) { s_acc[w][27] = accl[0]; s_acc[w][28] = accl[1]; }
   }
   __syncthreads();
-  if (threadIdx.x < NACC)
-    st->acc[threadIdx.x] = (s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x]);
+  if (threadIdx.x < NACC) partial[(long long)blockIdx.x * NACC + threadIdx.x] = tree_sum<NN_THREADS / 32>(s_acc, threadIdx.x);
+  __threadfence();
   __syncthreads();
-  if (w == 0) {  // convergence bookkeeping (uniform across the warp) + warp-parallel 6x6 solve
-    const int round = st->round;
-    const double cnt = st->acc[28];
-    const double f2 = cnt / (double)n_src;
-    const double e2 = cnt > 0.0 ? sqrt(st->acc[27] / cnt) : 0.0;
-    bool done = false;
-    int converged = 0;
-    if (round > 0 && fabs(st->fitness - f2) < rel_fitness && fabs(st->rmse - e2) < rel_rmse) {
-      converged = 1;
-      done = true;
-    }
-    if (!done && round >= max_iter) done = true;
-    // device-count mode: clouds below min_points are not registered (pose = initial guess)
-    const bool skipped = min_points > 0 && (n_src < min_points || hg_n(g) < min_points);
-    if (skipped) done = true;
-    double x[6] = {0, 0, 0, 0, 0, 0};
-    bool solved = false;
-    if (!done) solved = warp_solve6(st->acc, x, l);
-    __syncwarp();
-    if (l == 0) {
-      if (skipped) st->skipped = 1;
-      if (round > 0) st->iterations = round;  // this linearisation closes iteration `round`
-      if (converged) st->converged = 1;
-      st->fitness = f2;
-      st->rmse = e2;
-      if (!done && solved) {  // ill-posed -> identity update (R8)
-        double U[16], Tn[16], Tc[16];
-        for (int i = 0; i < 16; ++i) Tc[i] = st->T[i];
-        vec6_to_mat4(x, U);
-        mat4_mul(U, Tc, Tn);
-        for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
-      }
-      st->round = round + 1;
-      st->ticket = 0;
-      __threadfence();
-      st->done = done ? 1 : 0;
-    }
-  }
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) { st->dbg[1] = t_loop; st->dbg[2] = gtime(); }
+  icp_finish_round<NN_THREADS / 32>(st, partial, gridDim.x, n_src, g, min_points, max_iter, rel_fitness, rel_rmse, s_acc);
 }
 
 // correspondences as ORIGINAL target indices (t3d_icp_correspondences)
@@ -718,10 +867,8 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
     ctx->icp_offsets_ready = true;
   }
   HGrid g;
-  g.keys = ctx->scratch[0].as<unsigned long long>();
-  g.count = reinterpret_cast<unsigned*>(g.keys + hc);
-  g.start = g.count + hc;
-  g.fill = g.start + hc;
+  g.slots = ctx->scratch[0].as<HSlot>();
+  g.fill = reinterpret_cast<unsigned*>(g.slots + hc);
   g.near_keys = reinterpret_cast<unsigned long long*>(g.fill + hc);
   g.coarse_keys = g.near_keys + hc;
   g.mask = hc - 1;
@@ -731,17 +878,19 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   g.inv_h = 1.0 / g.h;
   g.n = n_tgt;
   g.n_dev = n_tgt_dev;
-  const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
-  // one CTA per SM: the work per round is tiny (one gather + 27 FMAs per point), what costs is the 29-double
-  // reduction tree per warp and the last CTA's pass over the per-CTA partials — both shrink with the grid
-  static int acc_mult = -1;
-  if (acc_mult < 0) { const char* e = getenv("T3D_ICP_ACC_MULT"); acc_mult = e ? atoi(e) : 1; if (acc_mult < 1) acc_mult = 1; }
-  const int grid_acc = (int)(want_acc < (long long)ctx->num_sms * acc_mult ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms * acc_mult);
+  // T3D_ICP_FUSE=0 (tuning): search and linearisation as two launches.  One search CTA per resident slot (4 per SM
+  // at 64 registers): the persistent loop covers the queries, and the last CTA's pass over the per-CTA partials
+  // shrinks with the grid.
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("T3D_ICP_FUSE"); fuse = (e && atoi(e) == 0) ? 0 : 1; }
   const long long want_nn = (n_src * NN_GROUP + NN_THREADS - 1) / NN_THREADS;
-  const int grid_nn = (int)(want_nn < (long long)ctx->num_sms * 8 ? (want_nn > 0 ? want_nn : 1) : (long long)ctx->num_sms * 8);
-  if ((rc = ctx->scratch[6].reserve(sizeof(double) * ((size_t)grid_acc * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
+  const int grid_nn = (int)(want_nn < (long long)ctx->num_sms * 4 ? (want_nn > 0 ? want_nn : 1) : (long long)ctx->num_sms * 4);
+  const long long want_acc = (n_src + ICP_THREADS - 1) / ICP_THREADS;
+  const int grid_acc = (int)(want_acc < (long long)ctx->num_sms ? (want_acc > 0 ? want_acc : 1) : (long long)ctx->num_sms);
+  const size_t part_rows = (size_t)(grid_nn > grid_acc ? grid_nn : grid_acc);
+  if ((rc = ctx->scratch[6].reserve(sizeof(double) * (part_rows * NACC) + sizeof(IcpState) + 64)) != T3D_OK) return rc;
   double* partial = ctx->scratch[6].as<double>();
-  IcpState* dst = reinterpret_cast<IcpState*>(partial + (size_t)grid_acc * NACC);
+  IcpState* dst = reinterpret_cast<IcpState*>(partial + part_rows * NACC);
   if ((rc = ctx->scratch[2].reserve(64)) != T3D_OK) return rc;
   g.cursor = ctx->scratch[2].as<unsigned>();
   if ((rc = ctx->scratch[3].reserve((size_t)n_src * 4)) != T3D_OK) return rc;
@@ -762,24 +911,25 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   // queries are far from the target (a bad initial guess, partial overlap).  Frame-to-model tracking
   // (device-count mode) registers a frame against the surface it was predicted from: nearly every query has
   // a target nearby, so the set's construction (a table scan + 27 inserts per coarse cell) is skipped.
-  const int near_filter = n_src_dev == nullptr ? 1 : 0;
+  const int near_filter = (n_src_dev == nullptr ? 1 : 0) | (getenv("T3D_ICP_DEBUG_NO_RING2") ? 2 : 0);
   auto enqueue_all = [&](int rounds, bool with_build) -> int {
     if (with_build) {
-      T3D_CUDA(cudaMemsetAsync(g.keys, 0xFF, hc * 8, st));
-      T3D_CUDA(cudaMemsetAsync(g.count, 0, hc * 12, st));
-      if (near_filter) T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
+      T3D_CUDA(cudaMemsetAsync(g.slots, 0, hc * 20, st));  // slots + fill
+      if (near_filter & 1) T3D_CUDA(cudaMemsetAsync(g.near_keys, 0xFF, hc * 16, st));  // near_keys + coarse_keys
       T3D_CUDA(cudaMemsetAsync(g.cursor, 0, 64, st));
       hg_count_kernel<<<bgrid, 256, 0, st>>>(tgt, g);
-      hg_alloc_kernel<<<hgrid, 256, 0, st>>>(g, near_filter);
-      if (near_filter) hg_dilate_kernel<<<hgrid, 256, 0, st>>>(g);
+      hg_alloc_kernel<<<hgrid, 256, 0, st>>>(g, near_filter & 1);
+      if (near_filter & 1) hg_dilate_kernel<<<hgrid, 256, 0, st>>>(g);
       hg_scatter_kernel<<<bgrid, 256, 0, st>>>(tgt, tgt_nrm, g);
       T3D_LAUNCH_CHECK();
       T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
     }
     for (int r = 0; r < rounds; ++r) {
-      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
-      icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, min_points, max_iter,
-                                                        rel_fitness, rel_rmse, dst, corr, corr_d2, partial);
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter,
+                                                    fuse, min_points, max_iter, rel_fitness, rel_rmse, partial);
+      if (!fuse)
+        icp_acc_kernel<<<grid_acc, ICP_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, min_points, max_iter,
+                                                          rel_fitness, rel_rmse, dst, corr, corr_d2, partial);
     }
     T3D_LAUNCH_CHECK();
     T3D_CUDA(cudaMemcpyAsync(hst, dst, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
@@ -789,14 +939,16 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
 
   if (out_idx) {  // t3d_icp_correspondences: one cold search at T0, optionally one warm search at T1
     if ((rc = enqueue_all(0, true)) != T3D_OK) return rc;
-    icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
+    icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter,
+                                                     0, 0, 0, 0.0, 0.0, partial);
     T3D_LAUNCH_CHECK();
     T3D_CUDA(cudaStreamSynchronize(st));
     if (T1) {
       for (int i = 0; i < 16; ++i) hst->T[i] = T1[i];
       hst->round = 1;
       T3D_CUDA(cudaMemcpyAsync(dst, hst, sizeof(IcpState), cudaMemcpyHostToDevice, st));
-      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter);
+      icp_nn_kernel<<<grid_nn, NN_THREADS, 0, st>>>(g, src, (long long)n_src, n_src_dev, r2, dst, corr, corr_d2, near_filter,
+                                                     0, 0, 0, 0.0, 0.0, partial);
     }
     icp_corr_export_kernel<<<(unsigned)((n_src + 255) / 256), 256, 0, st>>>(g, corr, corr_d2, (long long)n_src, out_idx, out_d2);
     T3D_LAUNCH_CHECK();
@@ -822,7 +974,7 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
     snprintf(key, sizeof(key), "icp|%p|%p|%p|%p|%p|%lld|%lld|%.17g|%d|%d|%.17g|%.17g|%p|%p|%p|%p|%p|%p|%d", (const void*)src,
              (const void*)n_src_dev, (const void*)tgt, (const void*)tgt_nrm, (const void*)n_tgt_dev, (long long)n_src,
              (long long)n_tgt, max_corr, max_iter, min_points, rel_fitness, rel_rmse, ctx->scratch[0].p,
-             ctx->scratch[1].p, ctx->scratch[2].p, ctx->scratch[3].p, ctx->scratch[4].p, ctx->scratch[6].p, first);
+             ctx->scratch[1].p, ctx->scratch[2].p, ctx->scratch[3].p, ctx->scratch[4].p, ctx->scratch[6].p, first + 100 * fuse);
     cudaGraphExec_t exec = nullptr;
     for (auto& cg : ctx->graphs)
       if (cg.key == key) exec = cg.exec;
@@ -853,14 +1005,14 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
   if (!launched) {
     if ((rc = enqueue_all(first, true)) != T3D_OK) return rc;
   }
-  ctx->launches += 4 + 2 * first;
+  ctx->launches += 4 + first * (fuse ? 1 : 2);
   enqueued = first;
   T3D_CUDA(cudaStreamSynchronize(st));
   while (!hst->done && enqueued < max_iter + 1) {
     int n = max_iter + 1 - enqueued;
-    if (n > 8) n = 8;
+    if (n > 4) n = 4;  // a finished round costs ~4.5 us as a no-op launch, a host round trip ~20 us
     if ((rc = enqueue_all(n, false)) != T3D_OK) return rc;
-    ctx->launches += 2 * n;
+    ctx->launches += n * (fuse ? 1 : 2);
     enqueued += n;
     T3D_CUDA(cudaStreamSynchronize(st));
   }
@@ -868,6 +1020,10 @@ static int icp_fused(t3d_ctx* ctx, const float* src, int64_t n_src, const long l
     t3d_set_error("icp: target coordinates exceed +-2^19 * max_corr_dist");
     return T3D_E_NUMERIC;
   }
+  if (getenv("T3D_ICP_TIMING"))
+    fprintf(stderr, "icp timing (last round, us): start->lastCTA loop end %.1f | ->ticket %.1f | ->partials summed %.1f | ->solved %.1f | ->state written %.1f  (rounds %d)\n",
+            (hst->dbg[1] - hst->dbg[0]) * 1e-3, (hst->dbg[2] - hst->dbg[1]) * 1e-3, (hst->dbg[3] - hst->dbg[2]) * 1e-3,
+            (hst->dbg[4] - hst->dbg[3]) * 1e-3, (hst->dbg[5] - hst->dbg[4]) * 1e-3, hst->round);
   for (int i = 0; i < 16; ++i) res->T[i] = hst->T[i];
   res->fitness = hst->fitness;
   res->inlier_rmse = hst->rmse;
