@@ -338,3 +338,23 @@ def test_overlap_order_puts_the_tail_first_and_the_head_last():
         for k in range(0, n, b):                                              # ascending inside every batch
             chunk = order[k:k + b]
             assert chunk == sorted(chunk)
+
+
+def test_tail_head_order_puts_the_tail_first_and_the_head_second():
+    """Frame order of the copy-engine router: the tail batch (the frames whose blocks travel) first, the head
+    batch (the frames that meet incoming blocks) second, the middle batches after them; every frame exactly once,
+    ascending inside a batch, and batch boundaries of the reordered sequence never split tail or head."""
+    for n, b in [(300, 64), (300, 32), (625, 64), (192, 64), (130, 64), (64, 64), (7, 3)]:
+        order = D.CopyEngineBlockRouter.tail_head_order(n, b)
+        assert sorted(order) == list(range(n))
+        tail = order[:min(b, n)]
+        assert tail == list(range(n - len(tail), n)) or n <= b                # the last frames of the slab, in order
+        if n >= 2 * b:
+            assert order[b:2 * b] == list(range(b))                           # the slab's first frames second
+            assert order[2 * b:] == list(range(b, n - b))                     # then the middle, in frame order
+        for k in range(0, n, b):
+            chunk = order[k:k + b]
+            assert chunk == sorted(chunk)
+    # the frames that reach past the slab (depth_max / advance + 2 = 22 at cfg 2) are all in the first batch
+    order = D.CopyEngineBlockRouter.tail_head_order(300, 64)
+    assert set(range(300 - 22, 300)) <= set(order[:64])
