@@ -333,15 +333,17 @@ class CopyEngineBlockRouter(P2PBlockRouter):
         self.last_counts = [0] * world
         self.route_events = []          # (start, end) CUDA events of every route, for bench.py
 
-    def _read_counts(self, n_blocks_dev):
-        """Enqueue the per-owner count on the current stream and read it on the host."""
-        import torch
+    def _enqueue_counts(self, n_blocks_dev):
+        """Enqueue the per-owner count and its copy to pinned host memory on the current stream (no host sync)."""
         from . import _lib
         from .runtime import _ptr, _stream
         _lib.check(self.lib.t3d_tsdf_route_counts_upto(self.vol.handle, self.AXIS, self.slab_blocks, self.world, self.rank,
                                                        _ptr(n_blocks_dev), _ptr(self.counts_dev), _stream()))
         self.counts_pin.copy_(self.counts_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+
+    def _counts_on_host(self):
+        """The counts of the last _enqueue_counts (the caller has synchronised with it); raises if a region is too small."""
+        from . import _lib
         counts = self.counts_pin.tolist()
         worst = max(counts)
         if worst > self.region_records:
@@ -349,6 +351,13 @@ class CopyEngineBlockRouter(P2PBlockRouter):
                                 f"CopyEngineBlockRouter: {worst} block records for one owner exceed the receive region "
                                 f"(region_records={self.region_records}); nothing was sent — raise region_records")
         return counts
+
+    def _read_counts(self, n_blocks_dev):
+        """Enqueue the per-owner count on the current stream and read it on the host."""
+        import torch
+        self._enqueue_counts(n_blocks_dev)
+        torch.cuda.current_stream().synchronize()
+        return self._counts_on_host()
 
     def _send(self, counts, n_blocks_dev):
         """pack -> per-destination peer copies -> fence, all on the current stream; returns the buffer parity."""
@@ -430,24 +439,32 @@ class CopyEngineBlockRouter(P2PBlockRouter):
         def hook(phase, ev_a, ev_b):
             h = C.c_void_p(side.cuda_stream)
             if phase == 0:
+                # the blocks that will travel exist once K4 of the tail batch is done: count them on the device.  The
+                # host does NOT wait here: K5's persistent CTAs own every SM, so the count kernel only runs when K5 of
+                # the tail batch retires, and a host that waits for it cannot enqueue the next batch meanwhile (the
+                # GPU then idles for the count, the host's pack / copy / fence calls and a whole K4).
                 with torch.cuda.stream(side):
-                    # the blocks that will travel exist once K4 of the tail batch is done: count them (host read) while
-                    # its K5 is still running ...
                     _lib.check(self.lib.t3d_stream_wait_event(h, ev_a))
-                    counts = self._read_counts(self._snap)
-                    # ... and pack / copy / fence behind that K5, underneath the fusion of the other batches
-                    _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
-                    state["e0"] = torch.cuda.Event(enable_timing=True)
-                    state["e0"].record()
-                    state["par"] = self._send(counts, self._snap)
+                    self._enqueue_counts(self._snap)
+                    state["counted"] = torch.cuda.Event()
+                    state["counted"].record()
+                state["k5_tail"] = ev_b
             elif phase == 1:
+                # K5 of the head batch is enqueued: the GPU is busy for two more batches.  Now read the counts (they
+                # arrive when K5 of the tail batch ends) and enqueue pack / copies / fence behind that K5 and the
+                # merge behind the head batch's K5 — the head batch is the only one that touches incoming blocks.
+                state["counted"].synchronize()
+                counts = self._counts_on_host()
                 with torch.cuda.stream(side):
-                    # the head batch is the only one that touches incoming blocks: merge once its K5 is done
+                    _lib.check(self.lib.t3d_stream_wait_event(h, state["k5_tail"]))
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    par = self._send(counts, self._snap)
                     _lib.check(self.lib.t3d_stream_wait_event(h, ev_b))
-                    self._merge_all(state["par"])
+                    self._merge_all(par)
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
-                    self.route_events.append((state["e0"], e1))
+                    self.route_events.append((e0, e1))
                 _lib.check(self.lib.t3d_event_record(self._done, h))
 
         self.vol.integrate_sequence_hooked(views_reordered, n_frames, H, W, batch, self._snap, hook, None,
