@@ -620,6 +620,22 @@ def measure_cfg3(args, ctx, F, steps, warmup, cpu_frames, stages=True):
         step()
         st = {k: v / F for k, v in trk.stage_ms.items()}
         trk.stage_ms = None
+    icp_roof = None
+    try:   # roofline of the ICP stage on SURVEY 8d's figure: 36 B per correspondence and iteration
+        regs = [r for r in trk.icp_log if r is not None]
+        corr_rounds = sum(int(r.correspondences) * (int(r.iterations) + 1) for r in regs)   # rounds = iterations + 1
+        if st and st.get("icp") and regs:
+            peak, peak_src = load_peaks()
+            icp_s = st["icp"] * 1e-3 * F                        # the stage pass tracked F frames
+            ach = 36.0 * corr_rounds / icp_s / 1e9
+            icp_roof = {"kernel": "icp_nn_kernel (K8: search + fused linearisation, one launch per round)", "bound": "hbm",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes": 36.0 * corr_rounds,
+                        "correspondence_rounds": corr_rounds, "registrations": len(regs),
+                        "note": "latency-bound hash-grid search on ~1e5 queries per round: the fraction says how far a "
+                                "frame-sized registration is from streaming, not that bandwidth limits it (DESIGN 7.4)"}
+    except Exception as e:  # noqa: BLE001
+        icp_roof = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if not args.no_cpu and cpu_frames > 0:
         from oracle import capi, ref_tracker
@@ -650,7 +666,7 @@ def measure_cfg3(args, ctx, F, steps, warmup, cpu_frames, stages=True):
                          "mean_icp_iterations": float(np.mean(its)) if its else None,
                          "mean_fitness": float(np.mean(fit)) if fit else None,
                          "last_target_points": trk.last_target[0]},
-            "cpu_baseline": cpu, "blocks": int(nblocks)}
+            "icp_roofline": icp_roof, "cpu_baseline": cpu, "blocks": int(nblocks)}
     del trk, depth_all, bgr_all
     torch.cuda.empty_cache()
     return line
@@ -675,8 +691,8 @@ def guarded(fn):
 def secondary_cfg3(args, ctx):
     """BASELINE configs[2] in short: 120 frames of the ICP + TSDF loop (the metric's "(TSDF+ICP)")."""
     r = measure_cfg3(args, ctx, 120, 1, 1, 4, stages=True)
-    keep = ("metric", "value", "unit", "ms_per_frame", "stage_ms_per_frame_synchronised", "tracking", "cpu_baseline",
-            "gpu_launches", "blocks")
+    keep = ("metric", "value", "unit", "ms_per_frame", "stage_ms_per_frame_synchronised", "icp_roofline", "tracking",
+            "cpu_baseline", "gpu_launches", "blocks")
     out = {k: r[k] for k in keep}
     out["workload"] = "BASELINE configs[2], first 120 of the 600 frames: frame-to-model point-to-plane ICP + TSDF fusion"
     return out
