@@ -137,11 +137,11 @@ int linearize(t3d_ctx* ctx, const GridDev& g, const float* src, long long n_src,
 
 // ===========================================================================
 // Device-resident registration: hashed target grid (no bounds pass, no sort) and
-// a registration state that lives in HBM.  Every iteration is two launches
-// (correspondences; accumulate + reduce + 6x6 solve by the last CTA) that turn
-// into no-ops once the state says "done", so the host enqueues a handful of
-// iterations at a time and reads one small result record back — no host round
-// trip, H2D pose upload or D2H reduction per iteration.
+// a registration state that lives in HBM.  Every iteration is ONE launch
+// (correspondences with the accumulation fused in; reduce + 6x6 solve by the
+// last CTA) that turns into a no-op once the state says "done", so the host
+// enqueues a handful of iterations at a time and reads one small result record
+// back — no host round trip, H2D pose upload or D2H reduction per iteration.
 // ===========================================================================
 
 namespace {
