@@ -263,6 +263,10 @@ int t3d_tsdf_integrate_sequence(t3d_tsdf* v, const t3d_frame_view* frames_h,
  *       completes with it (event_b is NULL).  The callee enqueues what must run between K4 and K5 of the last batch
  *       and records wait_before_last before returning;
  *   wait_before_last (cudaEvent_t, nullable): K5 of the last batch waits for it (without a hook: K4 too).
+ * The hook runs on the thread that feeds the pipeline: while it blocks (an event or stream synchronise) no later
+ * batch is enqueued.  K5's persistent CTAs own every SM, so work the hook enqueues behind K4 of batch b only runs
+ * when K5 of batch b retires — a hook that waits for such work in phase b stalls the GPU for a whole batch; wait
+ * one phase later, when the next batch is already queued (CopyEngineBlockRouter.fuse_overlapped does).
  * Needs at least 2 batches when any hook is given. */
 typedef void (*t3d_sequence_hook)(void* user, int phase, void* event_a, void* event_b);
 int t3d_tsdf_integrate_sequence_hooked(t3d_tsdf* v, const t3d_frame_view* frames_h,
